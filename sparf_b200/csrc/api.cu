@@ -1,0 +1,106 @@
+// C-ABI entry points that dispatch between MLP engines, plus library-level bookkeeping.
+#include <cstring>
+
+#include "common.cuh"
+#include "mlp_simt.cuh"
+#ifdef SPARF_WITH_TC
+#include "mlp_tc.cuh"
+#endif
+
+namespace sparf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static bool device_is_sm100() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10;
+}
+
+// AUTO -> the tensor-core engine when this MLP shape is covered by it, else SIMT
+static int resolve_engine(const SparfMLP* mlp, int engine) {
+#ifdef SPARF_WITH_TC
+  if (engine == SPARF_ENGINE_AUTO) return tc_supports(mlp) && device_is_sm100() ? SPARF_ENGINE_TC_3XBF16 : SPARF_ENGINE_SIMT_FP32;
+#else
+  if (engine == SPARF_ENGINE_AUTO) return SPARF_ENGINE_SIMT_FP32;
+#endif
+  return engine;
+}
+
+}  // namespace sparf
+
+using namespace sparf;
+
+extern "C" int sparf_version(void) { return SPARF_B200_VERSION; }
+extern "C" const char* sparf_last_error(void) { return g_err; }
+
+extern "C" int sparf_engine_available(int engine) {
+  if (engine == SPARF_ENGINE_SIMT_FP32) return 1;
+#ifdef SPARF_WITH_TC
+  if (engine == SPARF_ENGINE_TC_3XBF16 || engine == SPARF_ENGINE_TC_1XBF16) return device_is_sm100() ? 1 : 0;
+#endif
+  return 0;
+}
+
+extern "C" size_t sparf_mlp_workspace_bytes(const SparfMLP* mlp, int32_t R, int32_t S, int32_t backward, int32_t engine) {
+  if (!mlp || R <= 0 || S <= 0) return 0;
+  engine = resolve_engine(mlp, engine);
+#ifdef SPARF_WITH_TC
+  if (engine == SPARF_ENGINE_TC_3XBF16 || engine == SPARF_ENGINE_TC_1XBF16) return tc_workspace_bytes(mlp, R, S, backward, engine);
+#endif
+  return simt_workspace_bytes(mlp, R, S, backward);
+}
+
+extern "C" int sparf_mlp_forward(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S, const float* origins,
+                                 const float* dirs, const float* t, const float* noise, float* sigma, float* rgb,
+                                 void* workspace, size_t workspace_bytes, sparf_stream_t stream) {
+  SPARF_REQUIRE(mlp && R >= 0 && S > 0, "mlp_forward: bad arguments");
+  SPARF_REQUIRE(origins && dirs && t && sigma && rgb, "mlp_forward: NULL tensor");
+  if (R == 0) return SPARF_OK;
+  engine = resolve_engine(mlp, engine);
+  if (engine == SPARF_ENGINE_SIMT_FP32)
+    return simt_mlp_forward(mlp, R, S, origins, dirs, t, noise, sigma, rgb, workspace, workspace_bytes, (cudaStream_t)stream);
+#ifdef SPARF_WITH_TC
+  if (engine == SPARF_ENGINE_TC_3XBF16 || engine == SPARF_ENGINE_TC_1XBF16)
+    return tc_mlp_forward(mlp, engine, R, S, origins, dirs, t, noise, sigma, rgb, workspace, workspace_bytes, (cudaStream_t)stream);
+#endif
+  set_error("mlp_forward: engine %d not available in this build", engine);
+  return SPARF_ERR_UNSUPPORTED;
+}
+
+extern "C" int sparf_mlp_backward(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S, const float* origins,
+                                  const float* dirs, const float* t, const float* noise, const float* d_sigma,
+                                  const float* d_rgb, const SparfMLPGrad* grad, float* d_origins, float* d_dirs,
+                                  void* workspace, size_t workspace_bytes, sparf_stream_t stream) {
+  SPARF_REQUIRE(mlp && R >= 0 && S > 0, "mlp_backward: bad arguments");
+  SPARF_REQUIRE(origins && dirs && t && d_sigma && d_rgb && grad, "mlp_backward: NULL tensor");
+  if (R == 0) return SPARF_OK;
+  engine = resolve_engine(mlp, engine);
+  if (engine == SPARF_ENGINE_SIMT_FP32)
+    return simt_mlp_backward(mlp, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace, workspace_bytes, (cudaStream_t)stream);
+#ifdef SPARF_WITH_TC
+  if (engine == SPARF_ENGINE_TC_3XBF16 || engine == SPARF_ENGINE_TC_1XBF16)
+    return tc_mlp_backward(mlp, engine, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace, workspace_bytes, (cudaStream_t)stream);
+#endif
+  set_error("mlp_backward: engine %d not available in this build", engine);
+  return SPARF_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,309 @@
+"""torch.autograd adapters over the C ABI (include/sparf_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the stream and the autograd tape; every number is
+produced by the kernels in csrc/.  All functions take / return fp32 CUDA tensors and raise if the
+native library is unavailable (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SparfMLP, SparfMLPGrad, check
+
+_ENGINE = [_lib.ENGINE_AUTO]
+
+
+def set_engine(name_or_id) -> None:
+    """Select the MLP engine: 'auto' | 'simt_fp32' | 'tc_3xbf16' | 'tc_1xbf16'."""
+    _ENGINE[0] = _lib.ENGINES[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+
+
+def get_engine() -> int:
+    return _ENGINE[0]
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    assert t.is_cuda, "sparf_b200 ops need CUDA tensors (there is no CPU path)"
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# MLP description
+# ------------------------------------------------------------------------------------------------
+class MLPSpec:
+    """Static description of one NeRF network (shapes + c2f schedule), independent of the tensors."""
+
+    def __init__(self, n_trunk=8, width=256, head_width=128, skip_layer=4, L_xyz=10, L_view=4, barf_c2f=None):
+        self.n_trunk, self.width, self.head_width, self.skip_layer = n_trunk, width, head_width, skip_layer
+        self.L_xyz, self.L_view = L_xyz, L_view
+        self.barf_c2f = tuple(barf_c2f) if barf_c2f is not None else None
+
+    def n_params(self) -> int:
+        return 2 * self.n_trunk + 4
+
+    def fill(self, params: Sequence[torch.Tensor], progress: Optional[torch.Tensor]) -> Tuple[SparfMLP, list]:
+        """params = [trunk_w0, trunk_b0, ..., head_w0, head_b0, head_w1, head_b1] (nn.Linear tensors)."""
+        keep = [_f32c(p.detach()) for p in params]
+        m = SparfMLP()
+        m.n_trunk, m.width, m.head_width, m.skip_layer = self.n_trunk, self.width, self.head_width, self.skip_layer
+        m.L_xyz, m.L_view = self.L_xyz, self.L_view
+        m.use_c2f = 1 if self.barf_c2f is not None else 0
+        if self.barf_c2f is not None:
+            start, end = self.barf_c2f
+            m.c2f_start = float(start)
+            m.c2f_range = float(end - start)  # python-double subtraction, like the reference
+            assert progress is not None
+            prog = _f32c(progress.detach()).reshape(1)
+            keep.append(prog)
+            m.progress = prog.data_ptr()
+        else:
+            m.progress = 0
+        for i in range(self.n_trunk):
+            m.trunk_w[i] = keep[2 * i].data_ptr()
+            m.trunk_b[i] = keep[2 * i + 1].data_ptr()
+        o = 2 * self.n_trunk
+        m.head_w[0], m.head_b[0] = keep[o].data_ptr(), keep[o + 1].data_ptr()
+        m.head_w[1], m.head_b[1] = keep[o + 2].data_ptr(), keep[o + 3].data_ptr()
+        return m, keep
+
+    def grad_struct(self, grads: Sequence[torch.Tensor]) -> SparfMLPGrad:
+        g = SparfMLPGrad()
+        for i in range(self.n_trunk):
+            g.trunk_w[i] = grads[2 * i].data_ptr()
+            g.trunk_b[i] = grads[2 * i + 1].data_ptr()
+        o = 2 * self.n_trunk
+        g.head_w[0], g.head_b[0] = grads[o].data_ptr(), grads[o + 1].data_ptr()
+        g.head_w[1], g.head_b[1] = grads[o + 2].data_ptr(), grads[o + 3].data_ptr()
+        return g
+
+
+_WS = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch buffer (stream-ordered reuse is safe: one stream, no overlap)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# MLP: sigma, rgb = NeRF.forward_samples(o, d, t)
+# ------------------------------------------------------------------------------------------------
+class MLPFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec: MLPSpec, engine: int, origins, dirs, t, noise, progress, *params):
+        L = _lib.lib()
+        origins, dirs, t = _f32c(origins), _f32c(dirs), _f32c(t)
+        R, S = t.shape
+        assert origins.shape == (R, 3) and dirs.shape == (R, 3)
+        noise_c = _f32c(noise) if noise is not None else None
+        m, keep = spec.fill(params, progress)
+        sigma = torch.empty(R, S, device=t.device, dtype=torch.float32)
+        rgb = torch.empty(R, S, 3, device=t.device, dtype=torch.float32)
+        nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 0, engine)
+        ws = _workspace(nbytes, t.device)
+        check(L.sparf_mlp_forward(ctypes.byref(m), engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t), _ptr(noise_c),
+                                  _ptr(sigma), _ptr(rgb), _ptr(ws), ws.numel(), _stream()), "mlp_forward")
+        ctx.spec, ctx.engine = spec, engine
+        ctx.noise = noise_c
+        ctx.progress = progress
+        ctx.save_for_backward(origins, dirs, t, *params)
+        return sigma, rgb
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_rgb):
+        L = _lib.lib()
+        origins, dirs, t, *params = ctx.saved_tensors
+        spec = ctx.spec
+        R, S = t.shape
+        g_sigma = _f32c(g_sigma) if g_sigma is not None else torch.zeros(R, S, device=t.device)
+        g_rgb = _f32c(g_rgb) if g_rgb is not None else torch.zeros(R, S, 3, device=t.device)
+        m, keep = spec.fill(params, ctx.progress)
+        sizes = [p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), device=t.device, dtype=torch.float32)
+        grads, o = [], 0
+        for p, n in zip(params, sizes):
+            grads.append(flat[o:o + n].view(p.shape))
+            o += n
+        gs = spec.grad_struct(grads)
+        need_o, need_d = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        d_o = torch.zeros_like(origins) if (need_o or need_d) else None
+        d_d = torch.zeros_like(dirs) if (need_o or need_d) else None
+        nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 1, ctx.engine)
+        ws = _workspace(nbytes, t.device)
+        check(L.sparf_mlp_backward(ctypes.byref(m), ctx.engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t),
+                                   _ptr(ctx.noise), _ptr(g_sigma), _ptr(g_rgb), ctypes.byref(gs), _ptr(d_o), _ptr(d_d),
+                                   _ptr(ws), ws.numel(), _stream()), "mlp_backward")
+        return (None, None, d_o if need_o else None, d_d if need_d else None, None, None, None, *grads)
+
+
+def mlp_forward(spec: MLPSpec, origins, dirs, t, params: Sequence[torch.Tensor], *, noise=None, progress=None,
+                engine: Optional[int] = None):
+    """origins/dirs [R,3], t [R,S] -> (sigma [R,S], rgb [R,S,3]); differentiable w.r.t. origins, dirs, params."""
+    eng = get_engine() if engine is None else engine
+    return MLPFunction.apply(spec, eng, origins, dirs, t, noise, progress, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+class CompositeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sigma, rgb, t, dirs, white_bg: bool):
+        L = _lib.lib()
+        sigma, rgb, t, dirs = _f32c(sigma), _f32c(rgb), _f32c(t), _f32c(dirs)
+        R, S = t.shape
+        dev = t.device
+        rgb_map = torch.empty(R, 3, device=dev)
+        depth, opacity = torch.empty(R, device=dev), torch.empty(R, device=dev)
+        depth_var, rgb_var = torch.empty(R, device=dev), torch.empty(R, device=dev)
+        weights, all_cum = torch.empty(R, S, device=dev), torch.empty(R, device=dev)
+        check(L.sparf_composite_forward(R, S, _ptr(sigma), _ptr(rgb), _ptr(t), _ptr(dirs), int(white_bg), _ptr(rgb_map),
+                                        _ptr(depth), _ptr(opacity), _ptr(depth_var), _ptr(rgb_var), _ptr(weights),
+                                        _ptr(all_cum), _stream()), "composite_forward")
+        ctx.white_bg = bool(white_bg)
+        ctx.save_for_backward(sigma, rgb, t, dirs)
+        ctx.mark_non_differentiable(depth_var, rgb_var, all_cum)
+        return rgb_map, depth, opacity, weights, depth_var, rgb_var, all_cum
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_opacity, g_weights, *_unused):
+        L = _lib.lib()
+        sigma, rgb, t, dirs = ctx.saved_tensors
+        R, S = t.shape
+        opt = lambda g: _f32c(g) if g is not None else None
+        g_rgb, g_depth, g_opacity, g_weights = opt(g_rgb), opt(g_depth), opt(g_opacity), opt(g_weights)
+        d_sigma = torch.empty_like(sigma)
+        d_rgb = torch.empty_like(rgb)
+        d_dirs = torch.zeros_like(dirs) if ctx.needs_input_grad[3] else None
+        check(L.sparf_composite_backward(R, S, _ptr(sigma), _ptr(rgb), _ptr(t), _ptr(dirs), int(ctx.white_bg),
+                                         _ptr(g_rgb), _ptr(g_depth), _ptr(g_opacity), _ptr(g_weights), _ptr(d_sigma),
+                                         _ptr(d_rgb), _ptr(d_dirs), _stream()), "composite_backward")
+        return d_sigma, d_rgb, None, d_dirs, None
+
+
+def composite(sigma, rgb, t, dirs, white_bg=False):
+    """-> rgb_map [R,3], depth [R], opacity [R], weights [R,S], depth_var [R], rgb_var [R], all_cumulated [R]."""
+    return CompositeFunction.apply(sigma, rgb, t, dirs, bool(white_bg))
+
+
+# ------------------------------------------------------------------------------------------------
+# rays
+# ------------------------------------------------------------------------------------------------
+class RayGenFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose_w2c, intr_inv, W: int, ray_idx, pixels):
+        L = _lib.lib()
+        pose_w2c, intr_inv = _f32c(pose_w2c), _f32c(intr_inv)
+        B = pose_w2c.shape[0]
+        if pixels is not None:
+            pixels = _f32c(pixels)
+            per_image = int(pixels.dim() == 3)
+            n = pixels.shape[-2]
+            idx = None
+        else:
+            idx = ray_idx.to(torch.int64).contiguous()
+            per_image = int(idx.dim() == 2 and idx.shape[0] == B)
+            n = idx.shape[-1]
+        origins = torch.empty(B, n, 3, device=pose_w2c.device)
+        dirs = torch.empty(B, n, 3, device=pose_w2c.device)
+        check(L.sparf_raygen_forward(B, n, int(W), _ptr(pose_w2c), _ptr(intr_inv), _ptr(idx), _ptr(pixels), per_image,
+                                     _ptr(origins), _ptr(dirs), _stream()), "raygen_forward")
+        ctx.args = (B, n, int(W), per_image)
+        ctx.save_for_backward(pose_w2c, intr_inv, idx if idx is not None else torch.empty(0), pixels if pixels is not None else torch.empty(0))
+        ctx.has_idx = idx is not None
+        return origins, dirs
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        L = _lib.lib()
+        pose_w2c, intr_inv, idx, pixels = ctx.saved_tensors
+        B, n, W, per_image = ctx.args
+        d_pose = torch.zeros_like(pose_w2c)
+        g_o = _f32c(g_o) if g_o is not None else None
+        g_d = _f32c(g_d) if g_d is not None else None
+        check(L.sparf_raygen_backward(B, n, W, _ptr(pose_w2c), _ptr(intr_inv), _ptr(idx if ctx.has_idx else None),
+                                      _ptr(None if ctx.has_idx else pixels), per_image, _ptr(g_o), _ptr(g_d),
+                                      _ptr(d_pose), _stream()), "raygen_backward")
+        return d_pose, None, None, None, None
+
+
+def raygen(pose_w2c, intr, W: int, *, ray_idx=None, pixels=None):
+    """pose_w2c [B,3,4], intr [B,3,3] -> (center, ray) [B,n,3] at ray_idx ((n,)/(B,n) int) or float pixels."""
+    assert (ray_idx is None) != (pixels is None)
+    intr_inv = torch.linalg.inv(intr.detach().float())  # camera.py:318-319; intrinsics carry no gradient
+    return RayGenFunction.apply(pose_w2c, intr_inv, W, ray_idx, pixels)
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling (no gradient)
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sample_depth(R: int, S: int, near: float, rng: float, *, inverse=False, rand=None, far_per_ray=None, device=None):
+    L = _lib.lib()
+    device = device or (rand.device if rand is not None else far_per_ray.device)
+    t = torch.empty(R, S, device=device, dtype=torch.float32)
+    rand_c = _f32c(rand).reshape(R, S) if rand is not None else None
+    far_c = _f32c(far_per_ray).reshape(R) if far_per_ray is not None else None
+    check(L.sparf_sample_depth(R, S, float(near), float(rng), int(inverse), _ptr(rand_c), _ptr(far_c), _ptr(t), _stream()),
+          "sample_depth")
+    return t
+
+
+@torch.no_grad()
+def sample_pdf_merge(weights, t_coarse, u_mid, near: float, far: float):
+    """weights, t_coarse [R,S]; u_mid [S_fine] -> (t_fine [R,S_fine], t_all [R,S+S_fine] ascending)."""
+    L = _lib.lib()
+    weights, t_coarse, u_mid = _f32c(weights), _f32c(t_coarse), _f32c(u_mid)
+    R, S = weights.shape
+    Sf = u_mid.numel()
+    t_fine = torch.empty(R, Sf, device=weights.device)
+    t_all = torch.empty(R, S + Sf, device=weights.device)
+    check(L.sparf_sample_pdf_merge(R, S, Sf, float(near), float(far), _ptr(weights), _ptr(t_coarse), _ptr(u_mid),
+                                   _ptr(t_fine), _ptr(t_all), _stream()), "sample_pdf_merge")
+    return t_fine, t_all
+
+
+# ------------------------------------------------------------------------------------------------
+# photometric Huber loss
+# ------------------------------------------------------------------------------------------------
+class Huber2Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        L = _lib.lib()
+        pred_c, target_c = _f32c(pred), _f32c(target)
+        loss = torch.zeros((), device=pred.device)
+        d_pred = torch.empty_like(pred_c)
+        check(L.sparf_huber2_fwd_bwd(pred_c.numel(), _ptr(pred_c), _ptr(target_c), 1.0, _ptr(loss), _ptr(d_pred), _stream()),
+              "huber2")
+        ctx.save_for_backward(d_pred)
+        ctx.shape = pred.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_pred,) = ctx.saved_tensors
+        return (d_pred * g).view(ctx.shape), None
+
+
+def huber2(pred, target):
+    """2 * mean Huber(delta=0.5)(pred - target)   (base_losses.py:155-156)."""
+    return Huber2Function.apply(pred, target.expand_as(pred))

@@ -101,3 +101,94 @@ def check_grads(grads, gold, tol, report=None):
         worst = max(worst, e)
         assert e < tol, (k, e)
     return worst
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA path replay (GPU box only)
+# ------------------------------------------------------------------------------------------------
+class RandomReplayer:
+    """Feeds the reference's recorded draws to our Graph, which issues the same torch.rand /
+    torch.randn_like calls in the same order (see tests/golden/make_golden.py: RandomRecorder)."""
+
+    def __init__(self, gold):
+        self.rand = [torch.from_numpy(gold[k]) for k in sorted(k for k in gold if k.startswith("rand_"))]
+        self.randn = [torch.from_numpy(gold[k]) for k in sorted(k for k in gold if k.startswith("randn_"))]
+
+    def _rand(self, *shape, device=None, **kw):
+        x = self.rand.pop(0)
+        return x.to(device) if device is not None else x
+
+    def _randn_like(self, t, **kw):
+        return self.randn.pop(0).to(t.device)
+
+    def __enter__(self):
+        self._o = (torch.rand, torch.randn_like)
+        torch.rand, torch.randn_like = self._rand, self._randn_like
+        return self
+
+    def __exit__(self, *a):
+        torch.rand, torch.randn_like = self._o
+
+
+def build_graph(name, device="cuda"):
+    """Our Graph (+ pose net) loaded with the golden case's deterministic weights."""
+    from sparf_b200.renderer import Graph
+    from sparf_b200.poses_models import FirstTwoColunmnsPoseParameters
+
+    c, opt, data, ray_idx, pixels, sd, sd_fine, init_w2c, depth_max = common.case_inputs(name)
+    dev = torch.device(device)
+    for k in ("image", "intr", "pose", "depth_range", "idx"):
+        data[k] = data[k].to(dev)
+    if init_w2c is not None:
+        pose_net = FirstTwoColunmnsPoseParameters(opt, nbr_poses=c["B"], initial_poses_w2c=init_w2c.to(dev), device=dev)
+
+        class PoseGraph(Graph):
+            def __init__(self, opt, device, pose_net):
+                super().__init__(opt, device)
+                self.pose_net = pose_net
+
+            def get_w2c_pose(self, opt, data_dict, mode=None):
+                return self.pose_net.get_w2c_poses()
+
+        net = PoseGraph(opt, dev, pose_net.to(dev))
+    else:
+        net = Graph(opt, dev)
+    net.nerf.load_state_dict(sd)
+    if c["fine"]:
+        net.nerf_fine.load_state_dict(sd_fine)
+    net.to(dev).train()
+    mv = lambda x: x.to(dev) if x is not None else None
+    return net, c, opt, data, mv(ray_idx), mv(pixels), mv(depth_max)
+
+
+def replay_graph(name, engine="simt_fp32"):
+    """Run the CUDA path on a golden case exactly as make_golden.py ran the reference."""
+    import sparf_b200
+    from oracle import sparf_oracle as O
+
+    sparf_b200.set_engine(engine)
+    gold = load_golden(name)
+    net, c, opt, data, ray_idx, pixels, depth_max = build_graph(name)
+    with RandomReplayer(gold):
+        if c.get("to_max"):
+            pose = net.get_w2c_pose(opt, data, mode=c["mode"])
+            out = net.render_up_to_maxdepth_at_specific_pose_and_rays(
+                opt, data, pose, data.intr, c["H"], c["W"], depth_max=depth_max, iter=10, ray_idx=ray_idx, mode=c["mode"])
+        elif pixels is not None:
+            out = net.render_image_at_specific_rays(opt, data, iter=10, pixels=pixels, mode=c["mode"])
+        else:
+            out = net.render_image_at_specific_rays(opt, data, iter=10, ray_idx=ray_idx, mode=c["mode"])
+    if pixels is None and not c.get("to_max"):
+        loss = O.photometric_loss(out, data.image, ray_idx)   # the loss formula is the checker's, the render is ours
+    else:
+        loss = linear_probe_loss(out)
+    loss.backward()
+    grads = {}
+    nets = [("nerf", net.nerf)] + ([("nerf_fine", net.nerf_fine)] if c["fine"] else [])
+    for tag, m in nets:
+        for pname, p in m.named_parameters():
+            if pname != "progress":
+                grads["grad_%s.%s" % (tag, pname)] = p.grad
+    if hasattr(net, "pose_net"):
+        grads["grad_pose_embedding"] = net.pose_net.pose_embedding.grad
+    return out, loss, grads, gold
