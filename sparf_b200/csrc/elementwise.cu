@@ -240,7 +240,10 @@ __global__ void composite_fwd_kernel(int R, int S, const float* __restrict__ sig
       sd = mul_rn(sg[k], mul_rn(gap, len));
     }
     float incl = warp_incl_scan(sd, lane);
-    float excl = carry + (incl - sd);
+    // exclusive prefix by SHIFTING the inclusive scan: (incl - sd) would cancel catastrophically on the
+    // last sample, whose sd ~ 1e10 (frequency_nerf.py:304)
+    float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    float excl = carry + (lane == 0 ? 0.f : prev);
     carry += __shfl_sync(0xffffffffu, incl, 31);
     if (k < S) {
       float T = expf(-excl);
@@ -311,7 +314,10 @@ __global__ void composite_bwd_kernel(int R, int S, const float* __restrict__ sig
       sd = mul_rn(sg[k], mul_rn(gap, len));
     }
     float incl = warp_incl_scan(sd, lane);
-    float excl = carry + (incl - sd);
+    // exclusive prefix by SHIFTING the inclusive scan: (incl - sd) would cancel catastrophically on the
+    // last sample, whose sd ~ 1e10 (frequency_nerf.py:304)
+    float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    float excl = carry + (lane == 0 ? 0.f : prev);
     carry += __shfl_sync(0xffffffffu, incl, 31);
     if (k < S) {
       float T = expf(-excl), e = expf(-sd);
@@ -333,7 +339,8 @@ __global__ void composite_bwd_kernel(int R, int S, const float* __restrict__ sig
     int k = c * 32 + (31 - lane);  // lane 0 handles the LAST sample of the chunk
     float a = k < S ? A[k] : 0.f;
     float incl = warp_incl_scan(a, lane);  // sum over samples >= k within the chunk
-    float suf = suf_carry + (incl - a);    // strictly after k
+    float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    float suf = suf_carry + (lane == 0 ? 0.f : prev);  // strictly after k
     suf_carry += __shfl_sync(0xffffffffu, incl, 31);
     if (k < S) {
       float dsd = Bv[k] - suf;
