@@ -87,6 +87,8 @@ typedef struct SparfMLPGrad {
 /* ---------------------------------------------------------------- misc */
 int sparf_version(void);
 const char* sparf_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches) */
+uint64_t sparf_launch_count(void);
 /* 1 if the library was built with the tcgen05 engine and the current device is sm_100 */
 int sparf_engine_available(int engine);
 

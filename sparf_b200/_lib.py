@@ -36,6 +36,7 @@ _P = c_void_p
 _SIGNATURES = {
     "sparf_version": (c_int32, []),
     "sparf_last_error": (c_char_p, []),
+    "sparf_launch_count": (ctypes.c_uint64, []),
     "sparf_engine_available": (c_int32, [c_int32]),
     "sparf_raygen_forward": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P]),
     "sparf_raygen_backward": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P, _P]),

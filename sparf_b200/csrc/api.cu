@@ -10,6 +10,7 @@
 namespace sparf {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -52,6 +53,7 @@ using namespace sparf;
 
 extern "C" int sparf_version(void) { return SPARF_B200_VERSION; }
 extern "C" const char* sparf_last_error(void) { return g_err; }
+extern "C" uint64_t sparf_launch_count(void) { return g_launch_count; }
 
 extern "C" int sparf_engine_available(int engine) {
   if (engine == SPARF_ENGINE_SIMT_FP32) return 1;

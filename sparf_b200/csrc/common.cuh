@@ -21,8 +21,11 @@ void set_error(const char* fmt, ...);
     }                                                                                            \
   } while (0)
 
+// every kernel launch of the library goes through this macro: it also feeds sparf_launch_count()
+extern unsigned long long g_launch_count;
 #define SPARF_CHECK_LAUNCH(name)                                                                 \
   do {                                                                                           \
+    ++::sparf::g_launch_count;                                                                   \
     cudaError_t _e = cudaGetLastError();                                                         \
     if (_e != cudaSuccess) {                                                                     \
       ::sparf::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \

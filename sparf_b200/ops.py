@@ -16,6 +16,31 @@ from ._lib import SparfMLP, SparfMLPGrad, check
 
 _ENGINE = [_lib.ENGINE_AUTO]
 
+# optional device-side timing of the MLP kernels (bench.py roofline): CUDA events on the launching stream
+PROFILE_ON = [False]
+PROFILE = []
+
+
+class _timed:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if PROFILE_ON[0]:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE_ON[0]:
+            self.e1.record()
+            PROFILE.append((self.tag, self.e0, self.e1))
+
+
+def profile_total_ms(tag_prefix="mlp"):
+    """Sum of the recorded intervals (call after torch.cuda.synchronize())."""
+    torch.cuda.synchronize()
+    return sum(e0.elapsed_time(e1) for tag, e0, e1 in PROFILE if tag.startswith(tag_prefix))
+
 
 def set_engine(name_or_id) -> None:
     """Select the MLP engine: 'auto' | 'simt_fp32' | 'tc_3xbf16' | 'tc_1xbf16'."""
@@ -120,8 +145,9 @@ class MLPFunction(torch.autograd.Function):
         rgb = torch.empty(R, S, 3, device=t.device, dtype=torch.float32)
         nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 0, engine)
         ws = _workspace(nbytes, t.device)
-        check(L.sparf_mlp_forward(ctypes.byref(m), engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t), _ptr(noise_c),
-                                  _ptr(sigma), _ptr(rgb), _ptr(ws), ws.numel(), _stream()), "mlp_forward")
+        with _timed("mlp_forward"):
+            check(L.sparf_mlp_forward(ctypes.byref(m), engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t), _ptr(noise_c),
+                                      _ptr(sigma), _ptr(rgb), _ptr(ws), ws.numel(), _stream()), "mlp_forward")
         ctx.spec, ctx.engine = spec, engine
         ctx.noise = noise_c
         ctx.progress = progress
@@ -149,9 +175,10 @@ class MLPFunction(torch.autograd.Function):
         d_d = torch.zeros_like(dirs) if (need_o or need_d) else None
         nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 1, ctx.engine)
         ws = _workspace(nbytes, t.device)
-        check(L.sparf_mlp_backward(ctypes.byref(m), ctx.engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t),
-                                   _ptr(ctx.noise), _ptr(g_sigma), _ptr(g_rgb), ctypes.byref(gs), _ptr(d_o), _ptr(d_d),
-                                   _ptr(ws), ws.numel(), _stream()), "mlp_backward")
+        with _timed("mlp_backward"):
+            check(L.sparf_mlp_backward(ctypes.byref(m), ctx.engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t),
+                                       _ptr(ctx.noise), _ptr(g_sigma), _ptr(g_rgb), ctypes.byref(gs), _ptr(d_o), _ptr(d_d),
+                                       _ptr(ws), ws.numel(), _stream()), "mlp_backward")
         return (None, None, d_o if need_o else None, d_d if need_d else None, None, None, None, *grads)
 
 
