@@ -161,6 +161,12 @@ int sparf_composite_backward(int32_t R, int32_t S, const float* sigma, const flo
 int sparf_huber2_fwd_bwd(int64_t n, const float* pred, const float* target, float scale, float* loss,
                          float* d_pred, sparf_stream_t stream);
 
+/* ---------------------------------------------------------------- diagnostics
+ * Minimal tcgen05 GEMM exercising every Blackwell primitive of the tensor-core engine (operand layout,
+ * descriptors, bulk copy, TMEM): D[128,128] = bf16(A[128,K]) * bf16(B[128,K])^T, K in {64,...,256}.
+ * `packed` is >= 128*K*2 bytes of scratch.  Used by tests/test_tc_engine.py. */
+int sparf_tc_selftest(const float* A, const float* B, int32_t K, void* packed, float* D, sparf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,104 @@
+// Minimal tcgen05 GEMM used to validate, on hardware, every primitive the tensor-core engine relies on:
+// SWIZZLE_128B operand images (written by generic stores AND pre-packed + bulk-copied), shared-memory /
+// instruction descriptors, K stepping inside the swizzle atom, commit -> mbarrier, TMEM loads.
+//   D[128, 128] = A[128, K] * B[128, K]^T,  K = 128, operands rounded to bf16, fp32 accumulate.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace sparf {
+using namespace tc;
+
+// B [128, K] fp32 row-major -> packed bf16 SW128 blocks, block kb = columns [64 kb, 64 kb + 64)
+__global__ void selftest_pack_kernel(const float* __restrict__ B, int K, uint8_t* __restrict__ packed) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * K) return;
+  int n = idx / K, k = idx % K;
+  int kb = k / kBlockK, kl = k % kBlockK;
+  __nv_bfloat16 v = __float2bfloat16_rn(B[idx]);
+  *reinterpret_cast<__nv_bfloat16*>(packed + (size_t)kb * 16384 + sw128_offset(n, kl)) = v;
+}
+
+__global__ void __launch_bounds__(128) selftest_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Bpacked,
+                                                             int K, float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nkb = K / kBlockK;
+  uint8_t* sA = smem;                       // nkb blocks of 16 KB
+  uint8_t* sB = smem + (size_t)nkb * 16384;  // nkb blocks of 16 KB
+  __shared__ uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(&bar_b, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 128);
+    tmem_relinquish();
+  }
+  // A: thread = row, generic 16-byte stores of 8 bf16 at the swizzled position
+  for (int kb = 0; kb < nkb; ++kb) {
+    for (int c = 0; c < 8; ++c) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a0 = A[(size_t)tid * K + kb * 64 + c * 8 + 2 * e], a1 = A[(size_t)tid * K + kb * 64 + c * 8 + 2 * e + 1];
+        __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+        w[e] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(sA + (size_t)kb * 16384 + sw128_offset(tid, c * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_b, (uint32_t)nkb * 16384u);
+    for (int kb = 0; kb < nkb; ++kb) bulk_g2s(sB + (size_t)kb * 16384, Bpacked + (size_t)kb * 16384, 16384u, &bar_b);
+    mbar_wait(&bar_b, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc(128, 128, 1);
+    for (int kb = 0; kb < nkb; ++kb) {
+      for (int ks = 0; ks < 4; ++ks) {
+        uint64_t da = make_smem_desc(smem_u32(sA + (size_t)kb * 16384) + ks * 32);
+        uint64_t db = make_smem_desc(smem_u32(sB + (size_t)kb * 16384) + ks * 32);
+        umma_ss(tmem_base, da, db, idesc, (kb | ks) != 0);
+      }
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(size_t)tid * 128 + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace sparf
+
+using namespace sparf;
+
+// A [128,K], B [128,K] fp32 device, K in {64,128,192,256}; packed: >= 128*K*2 bytes scratch; D [128,128] out.
+extern "C" int sparf_tc_selftest(const float* A, const float* B, int32_t K, void* packed, float* D, sparf_stream_t stream) {
+  SPARF_REQUIRE(K % 64 == 0 && K >= 64 && K <= 256, "tc_selftest: K=%d", K);
+  cudaStream_t st = (cudaStream_t)stream;
+  selftest_pack_kernel<<<ceil_div(128 * K, 256), 256, 0, st>>>(B, K, (uint8_t*)packed);
+  SPARF_CHECK_LAUNCH("selftest_pack_kernel");
+  size_t smem = (size_t)2 * (K / 64) * 16384 + 1024;
+  SPARF_CHECK_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_gemm_kernel<<<1, 128, smem, st>>>(A, (const uint8_t*)packed, K, D);
+  SPARF_CHECK_LAUNCH("selftest_gemm_kernel");
+  return SPARF_OK;
+}
