@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the SPARF ray-marching hot path (BASELINE.json metric: rays/s, fwd+bwd, 128 samples/ray).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|simt_fp32|tc_3xbf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|simt_fp32|tc_3x]
 
 One "step" = one pass of the hot path over one synthetic ray batch of BASELINE config 2 ("DTU 3-view,
 fixed GT poses, 1024 rays x 128 samples": 3 x 341 = 1023 rays of 300x400 views, coarse network):

@@ -44,8 +44,9 @@ enum {
 enum {
   SPARF_ENGINE_AUTO = 0,
   SPARF_ENGINE_SIMT_FP32 = 1, /* CUDA-core FFMA, fp32 throughout (bit-level twin of the reference) */
-  SPARF_ENGINE_TC_3XBF16 = 2, /* tcgen05, error-compensated 3-pass bf16 split, fp32 TMEM accumulate */
-  SPARF_ENGINE_TC_1XBF16 = 3  /* tcgen05, single bf16 pass ("fast", NOT within the 1e-4 parity bound) */
+  SPARF_ENGINE_TC_3X = 2, /* tcgen05: x*W = x_hi*W_hi + x_lo*W_hi + x_hi*W_lo on 16-bit halves (fp16 in the
+                             forward, bf16 for gradients), fp32 TMEM accumulation: the parity engine */
+  SPARF_ENGINE_TC_1X = 3  /* tcgen05, single 16-bit pass ("fast", NOT within the 1e-4 parity bound) */
 };
 
 typedef void* sparf_stream_t; /* cudaStream_t */

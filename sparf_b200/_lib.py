@@ -10,8 +10,8 @@ from . import build as _build
 
 MAX_TRUNK = 12
 
-ENGINE_AUTO, ENGINE_SIMT_FP32, ENGINE_TC_3XBF16, ENGINE_TC_1XBF16 = 0, 1, 2, 3
-ENGINES = {"auto": 0, "simt_fp32": 1, "tc_3xbf16": 2, "tc_1xbf16": 3}
+ENGINE_AUTO, ENGINE_SIMT_FP32, ENGINE_TC_3X, ENGINE_TC_1X = 0, 1, 2, 3
+ENGINES = {"auto": 0, "simt_fp32": 1, "tc_3x": 2, "tc_1x": 3}
 
 
 class SparfMLP(ctypes.Structure):

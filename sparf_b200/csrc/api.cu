@@ -40,7 +40,8 @@ static bool device_is_sm100() {
 // AUTO -> the tensor-core engine when this MLP shape is covered by it, else SIMT
 static int resolve_engine(const SparfMLP* mlp, int engine) {
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_AUTO) return tc_supports(mlp) && device_is_sm100() ? SPARF_ENGINE_TC_3XBF16 : SPARF_ENGINE_SIMT_FP32;
+  if (engine == SPARF_ENGINE_AUTO) return tc_supports(mlp) && device_is_sm100() ? SPARF_ENGINE_TC_3X : SPARF_ENGINE_SIMT_FP32;
+  if ((engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X) && !tc_supports(mlp)) return -1;
 #else
   if (engine == SPARF_ENGINE_AUTO) return SPARF_ENGINE_SIMT_FP32;
 #endif
@@ -58,7 +59,7 @@ extern "C" uint64_t sparf_launch_count(void) { return g_launch_count; }
 extern "C" int sparf_engine_available(int engine) {
   if (engine == SPARF_ENGINE_SIMT_FP32) return 1;
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3XBF16 || engine == SPARF_ENGINE_TC_1XBF16) return device_is_sm100() ? 1 : 0;
+  if (engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X) return device_is_sm100() ? 1 : 0;
 #endif
   return 0;
 }
@@ -67,7 +68,7 @@ extern "C" size_t sparf_mlp_workspace_bytes(const SparfMLP* mlp, int32_t R, int3
   if (!mlp || R <= 0 || S <= 0) return 0;
   engine = resolve_engine(mlp, engine);
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3XBF16 || engine == SPARF_ENGINE_TC_1XBF16) return tc_workspace_bytes(mlp, R, S, backward, engine);
+  if (engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X) return tc_workspace_bytes(mlp, R, S, backward, engine);
 #endif
   return simt_workspace_bytes(mlp, R, S, backward);
 }
@@ -82,7 +83,7 @@ extern "C" int sparf_mlp_forward(const SparfMLP* mlp, int32_t engine, int32_t R,
   if (engine == SPARF_ENGINE_SIMT_FP32)
     return simt_mlp_forward(mlp, R, S, origins, dirs, t, noise, sigma, rgb, workspace, workspace_bytes, (cudaStream_t)stream);
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3XBF16 || engine == SPARF_ENGINE_TC_1XBF16)
+  if (engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X)
     return tc_mlp_forward(mlp, engine, R, S, origins, dirs, t, noise, sigma, rgb, workspace, workspace_bytes, (cudaStream_t)stream);
 #endif
   set_error("mlp_forward: engine %d not available in this build", engine);
@@ -100,7 +101,7 @@ extern "C" int sparf_mlp_backward(const SparfMLP* mlp, int32_t engine, int32_t R
   if (engine == SPARF_ENGINE_SIMT_FP32)
     return simt_mlp_backward(mlp, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace, workspace_bytes, (cudaStream_t)stream);
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3XBF16 || engine == SPARF_ENGINE_TC_1XBF16)
+  if (engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X)
     return tc_mlp_backward(mlp, engine, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace, workspace_bytes, (cudaStream_t)stream);
 #endif
   set_error("mlp_backward: engine %d not available in this build", engine);

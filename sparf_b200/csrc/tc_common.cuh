@@ -10,6 +10,7 @@
 // of each row; stepping K inside the 128-byte row = adding 32 bytes to the descriptor start address.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -134,14 +135,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------- splitting
-// v = hi + lo + O(2^-17 |v|) with hi, lo in bf16: the error-compensated operand representation.
+// Error-compensated operand representation v = hi + lo.
+//   kF16 (forward): fp16 halves, 11 + 11 significant bits -> |v - hi - lo| <~ 2^-22 |v| (fp32-like); the
+//                   conversion saturates at +-65504 (NeRF activations / weights are O(1..1e2)).
+//   bf16 (backward): bf16 halves, 8 + 8 bits, 2^-17 relative, full fp32 exponent range for tiny gradients.
+template <bool kF16>
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);            // .x = a (low 16 bits), .y = b
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  float ra = a - __uint_as_float(hi << 16);
-  float rb = b - __uint_as_float(hi & 0xFFFF0000u);
-  __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
-  lo = *reinterpret_cast<uint32_t*>(&l);
+  if (kF16) {
+    uint32_t h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));   // low half = a
+    hi = h;
+    float2 hf = __half22float2(*reinterpret_cast<__half2*>(&h));
+    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+  } else {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);            // .x = a (low 16 bits), .y = b
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    float ra = a - __uint_as_float(hi << 16);
+    float rb = b - __uint_as_float(hi & 0xFFFF0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+  }
+}
+// scalar version for the weight packers: part 0 = hi, 1 = lo; returns the 16-bit pattern
+template <bool kF16>
+__device__ __forceinline__ uint16_t split1(float v, int part) {
+  if (kF16) {
+    __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    __half o = part == 0 ? h : __float2half_rn(v - __half2float(h));
+    return *reinterpret_cast<uint16_t*>(&o);
+  } else {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 o = part == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
+    return *reinterpret_cast<uint16_t*>(&o);
+  }
 }
 
 }  // namespace tc

@@ -43,7 +43,7 @@ def profile_total_ms(tag_prefix="mlp"):
 
 
 def set_engine(name_or_id) -> None:
-    """Select the MLP engine: 'auto' | 'simt_fp32' | 'tc_3xbf16' | 'tc_1xbf16'."""
+    """Select the MLP engine: 'auto' | 'simt_fp32' | 'tc_3x' | 'tc_1x'."""
     _ENGINE[0] = _lib.ENGINES[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
 
 

@@ -19,7 +19,7 @@ from helpers import check_grads, load_golden, rel_err, replay_graph
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = ["simt_fp32"]
+ENGINES = ["simt_fp32", "tc_3x"]   # fp32 CUDA-core engine and the tcgen05 split-precision engine
 
 
 def _dev(x):
