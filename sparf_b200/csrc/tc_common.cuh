@@ -99,10 +99,27 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 
-// 32-bit instruction descriptor, kind::f16, fp32 accumulate, A and B K-major.  fmt: 0 = f16, 1 = bf16.
-// (cute::UMMA::InstrDescriptor: c_format[4,6)=1 | a_format[7,10) | b_format[10,13) | n>>3 [17,23) | m>>4 [24,29))
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major SWIZZLE_128B descriptor: the SAME byte image as above ([rows x 64] with 128-byte rows), but read
+// with the 64 contiguous elements of a row as the M/N dimension and the rows as K (used by the weight-
+// gradient GEMM dW = G^T X, whose reduction runs over sample rows).  In CUTLASS terms
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = byte distance between consecutive 64-element
+// groups along M/N (here: between [rows x 64] blocks), SBO = distance between 8-row groups along K = 1024.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(kAtomBytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// 32-bit instruction descriptor, kind::f16, fp32 accumulate.  fmt: 0 = f16, 1 = bf16; major: 0 = K, 1 = MN.
+// (cute::UMMA::InstrDescriptor: c_format[4,6)=1 | a_format[7,10) | b_format[10,13) | a_major 15 | b_major 16 |
+//  n>>3 [17,23) | m>>4 [24,29))
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.

@@ -86,9 +86,86 @@ __global__ void __launch_bounds__(128) selftest_gemm_kernel(const float* __restr
   if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
+// "TN" GEMM with MN-major operands (the weight-gradient shape):
+//   D[128 (m), 128 (n)] = sum_{r < rows} G[r][m] * X[r][n],   G, X: [rows, 128] fp32 row-major, rows in {64, 128}
+// Both operands are written as the forward A-operand image ([rows x 64] blocks, sw128_offset(row, col)) and
+// consumed through MN-major descriptors.
+__global__ void __launch_bounds__(128) selftest_tn_kernel(const float* __restrict__ G, const float* __restrict__ X, int rows,
+                                                           float* __restrict__ D) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sG = smem;              // 2 feature blocks x 16 KB
+  uint8_t* sX = smem + 2 * 16384;  // 2 feature blocks x 16 KB
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 128);
+    tmem_relinquish();
+  }
+  // thread = sample row: 16-byte stores of 8 consecutive features
+  for (int src = 0; src < 2; ++src) {
+    const float* S = src == 0 ? G : X;
+    uint8_t* dst = src == 0 ? sG : sX;
+    for (int fb = 0; fb < 2; ++fb) {
+      for (int c = 0; c < 8; ++c) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (tid < rows) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(S[(size_t)tid * 128 + fb * 64 + c * 8 + 2 * e],
+                                                     S[(size_t)tid * 128 + fb * 64 + c * 8 + 2 * e + 1]);
+            w[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)fb * 16384 + sw128_offset(tid, c * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, 128, 1, 1, 1);
+    for (int ks = 0; ks < rows / 16; ++ks) {   // 16 sample rows = two 8-row atoms = 2048 bytes
+      uint64_t da = make_smem_desc_mn(smem_u32(sG) + ks * 2048, 16384);
+      uint64_t db = make_smem_desc_mn(smem_u32(sX) + ks * 2048, 16384);
+      umma_ss(tmem_base, da, db, idesc, ks != 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(size_t)tid * 128 + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
 }  // namespace sparf
 
 using namespace sparf;
+
+extern "C" int sparf_tc_selftest_tn(const float* G, const float* X, int32_t rows, float* D, sparf_stream_t stream) {
+  SPARF_REQUIRE(rows == 64 || rows == 128, "tc_selftest_tn: rows=%d", rows);
+  size_t smem = (size_t)4 * 16384 + 1024;
+  SPARF_CHECK_CUDA(cudaFuncSetAttribute(selftest_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_tn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, X, rows, D);
+  SPARF_CHECK_LAUNCH("selftest_tn_kernel");
+  return SPARF_OK;
+}
 
 // A [128,K], B [128,K] fp32 device, K in {64,128,192,256}; packed: >= 128*K*2 bytes scratch; D [128,128] out.
 extern "C" int sparf_tc_selftest(const float* A, const float* B, int32_t K, void* packed, float* D, sparf_stream_t stream) {

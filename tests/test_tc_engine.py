@@ -86,3 +86,19 @@ def test_tc_single_pass_is_a_fast_mode_outside_the_bound():
     e = (c_1 - c_ref).abs().max().item()
     print("single-pass bf16 rgb abs err %.2e" % e)
     assert e < 5e-2
+
+
+@pytest.mark.parametrize("rows", [64, 128])
+def test_tcgen05_selftest_tn_mn_major(rows):
+    """D = G^T X through MN-major descriptors on the forward's operand image (weight-gradient GEMM shape)."""
+    from sparf_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cpu").manual_seed(rows)
+    G = torch.randint(-4, 5, (rows, 128), generator=g).float().cuda()
+    X = torch.randint(-4, 5, (rows, 128), generator=g).float().cuda()
+    D = torch.full((128, 128), -777.0, device="cuda")
+    _lib.check(L.sparf_tc_selftest_tn(_p(G), _p(X), rows, _p(D), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "tc_selftest_tn")
+    torch.cuda.synchronize()
+    ref = G.t() @ X
+    assert torch.equal(D, ref), (D - ref).abs().max().item()
