@@ -1,21 +1,30 @@
-// tcgen05 engine for the NeRF MLP (SPARF_ENGINE_TC_3X / TC_1X).
+// tcgen05 engine for the NeRF MLP (SPARF_ENGINE_TC_3X / TC_1X), sm_100a.
 //
-// FORWARD: one persistent, warp-specialised kernel.  A CTA owns 128 sample rows at a time (one TMEM lane
-// per row) and pushes them through all 9 tensor-core layers without the activations ever leaving the SM:
-//
-//   warp 0      weight producer : streams pre-packed bf16 (hi | lo) weight blocks, 16 KB each, from L2 into a
+// FORWARD  (tc_mlp_fwd_kernel): one persistent, warp-specialised kernel.  A CTA owns 128 sample rows at a
+// time (one TMEM lane per row) and pushes them through all 9 tensor-core layers without the activations
+// leaving the SM:
+//   warp 0      weight producer : streams pre-packed 16-bit (hi | lo) weight blocks, 16 KB each, from L2 into a
 //                                 3-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx
 //   warp 1      MMA issuer      : one thread issues tcgen05.mma (M=128, N=128, K=16) into one of TWO 256-column
 //                                 fp32 TMEM accumulators (ping-pong per layer), commits to mbarriers
 //   warps 2-9   epilogue        : positional encoding -> A operand; per layer TMEM -> registers -> bias/ReLU ->
-//                                 (hi, lo) bf16 split -> next layer's A operand in shared memory, handed to the
-//                                 MMA warp per 64-column K block so layer l+1 starts while layer l drains;
-//                                 density row, colour head (128->3) and activations in fp32 on CUDA cores
+//                                 (hi, lo) split -> next layer's A operand in shared memory, handed to the MMA
+//                                 warp per 64-column K block so layer l+1 starts while layer l drains; density
+//                                 row, colour head (128->3) and activations in fp32 on CUDA cores
 //
-// PRECISION: x*W is evaluated as x_hi*W_hi + x_lo*W_hi + x_hi*W_lo with bf16 operands and fp32 accumulation
-// (error-compensated split, ~2^-17 relative per product; SURVEY.md hard part 1).  TC_1X keeps only
-// the first term.  The first layer's inputs (x = o + t d, sin/cos of x * 2^j pi) are computed with the
-// reference's exact fp32 op sequence before the split.
+// BACKWARD (tc_mlp_backward): nothing is kept from the forward call; per row chunk
+//   1. the forward kernel re-runs in bf16 "save" mode and dumps every layer's A-operand image to HBM,
+//   2. tc_mlp_dgrad_kernel (same skeleton, transposed weights) chains dL/dz_l from the colour head down to
+//      layer 0, ReLU masks read from the saved images, and dumps each dL/dz_l image,
+//   3. tc_mlp_wgrad_kernel computes dW_l = (dL/dz_l)^T x_l over the row chunk: the saved images are consumed
+//      AS THEY ARE through MN-major descriptors (reduction over rows), fp32 accumulation in TMEM, one
+//      atomic flush per CTA,
+//   4. small CUDA-core kernels finish biases, the density row, the 128->3 head and the view-direction part.
+//
+// PRECISION: x*W = x_hi*W_hi + x_lo*W_hi + x_hi*W_lo with 16-bit operand halves and fp32 accumulation
+// (SURVEY.md hard part 1).  Forward halves are fp16 (2^-22 relative: fp32-like), backward halves are bf16
+// (2^-17, full exponent range for tiny gradients).  TC_1X keeps only the first term.  The first layer's
+// inputs (x = o + t d, sin/cos of x * 2^j pi) use the reference's exact fp32 op sequence before the split.
 //
 // Reference: NeRF.forward_samples / forward / compute_raw_density (source/models/frequency_nerf.py:149-281).
 #include <algorithm>
@@ -35,22 +44,25 @@ constexpr int kHW = 128;         // head width
 constexpr int kL = 10;           // L_xyz
 constexpr int kLv = 4;           // L_view
 constexpr int kEv = 27;
-constexpr int kNumLayers = 9;    // tensor-core layers: trunk 0..7 + head 0
+constexpr int kNumLayers = 9;    // forward tensor-core layers: trunk 0..7 + head 0
+constexpr int kNumBwdLayers = 8; // backward tensor-core layers
 constexpr int kTileM = 128;
 constexpr int kStages = 3;
-constexpr int kChunkBytes = 16384;  // one [128 x 64] bf16 operand block
+constexpr int kChunkBytes = 16384;  // one [128 x 64] 16-bit operand block
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // 320
-constexpr int kChunksPerTile = 128;
-constexpr bool kFwdF16 = true;   // forward operands: fp16 (hi | lo) halves, see tc_common.cuh split2
+constexpr int kChunksPerTile = 128;     // forward weight chunks per tile
+constexpr int kBwdChunksPerTile = 120;  // backward (transposed) weight chunks per tile
 
-// K blocks of a layer: enc first (available early), then the 4 activation blocks
+// forward: K blocks of a layer: enc first (available early), then the 4 activation blocks
 __host__ __device__ constexpr int layer_nkb(int l) { return l == 0 ? 1 : (l == 4 ? 5 : 4); }
 __host__ __device__ constexpr int layer_nh(int l) { return l == 8 ? 1 : 2; }     // N / 128
 __host__ __device__ constexpr bool kb_is_enc(int l, int kbi) { return l == 0 || (l == 4 && kbi == 0); }
 __host__ __device__ constexpr int kb_act_index(int l, int kbi) { return l == 4 ? kbi - 1 : kbi; }
+// backward layer bl: 0: g_hid(128) -> g_featpre ; 1: g_featpre -> G6 ; 2..7: G_l -> G_{l-1}, l = 8 - bl
+__host__ __device__ constexpr int bwd_nkb(int bl) { return bl == 0 ? 2 : 4; }
 
-// ---- shared memory map (offsets from a 1024-aligned base)
+// ---- shared memory map of the chain kernels (offsets from a 1024-aligned base)
 constexpr int kOffAct = 0;                               // 8 blocks: hi kb0..3, lo kb0..3
 constexpr int kOffEnc = kOffAct + 8 * kChunkBytes;       // 2 blocks: hi, lo
 constexpr int kOffRing = kOffEnc + 2 * kChunkBytes;      // kStages blocks
@@ -63,6 +75,18 @@ constexpr int kOffBar = kOffPart + 2 * 128 * 4 * 4;      // mbarriers
 constexpr int kNumBars = 2 * kStages + 5 + 4;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget exceeded");
+
+// ---- saved operand images (HBM): tensor t, tile, 64-column block, part (hi | lo): 16 KB each
+enum { T_ENC = 0, T_H0 = 1, T_FEAT = 8, T_HID = 9, T_GHID = 10, T_G7F = 11, T_G6 = 12, T_G0 = 18, T_COUNT = 19 };
+__host__ __device__ constexpr int tensor_nblk(int t) { return t == T_ENC ? 1 : ((t == T_HID || t == T_GHID) ? 2 : 4); }
+__host__ __device__ constexpr int t_g(int l) { return T_G6 + (6 - l); }   // image of dL/dz_l, l = 0..6
+struct Images {
+  uint8_t* base;
+  size_t off[T_COUNT];
+  __host__ __device__ uint8_t* at(int t, int tile, int blk, int part) const {
+    return base + off[t] + ((((size_t)tile * tensor_nblk(t)) + blk) * 2 + part) * kChunkBytes;
+  }
+};
 
 struct FwdParams {
   const uint8_t* packed;   // kChunksPerTile chunks of 16 KB
@@ -78,10 +102,27 @@ struct FwdParams {
   const float* w9;         // [3,128]
   const float* b9;
   C2F c2f;
-  long long M;             // R*S rows
+  long long M;             // rows of this launch
   int S;
   int num_tiles;
   int passes;              // 3 (compensated) or 1
+  int save;                // dump A-operand images
+  Images img;
+};
+
+struct BwdParams {
+  const uint8_t* packed;   // kBwdChunksPerTile transposed chunks
+  const float* d_sigma;    // [M]
+  const float* d_rgb;      // [M,3]
+  const float* sigma;      // recomputed forward outputs
+  const float* rgb;
+  float* g_raw;            // [M]   dL/d raw density
+  float* g_pre;            // [M,4] dL/d colour pre-activation
+  const float* w7;         // [257,256] (row 0 = density row)
+  const float* w9;         // [3,128]
+  long long M;
+  int num_tiles;
+  Images img;
 };
 
 // reference column of internal encoder column ic (frequency_nerf.py:65-68 layout), -1 = zero pad
@@ -94,16 +135,17 @@ __host__ __device__ inline int enc_ref_col(int ic) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight packing: fp32 nn.Linear tensors -> bf16 (hi | lo) SW128 operand blocks in stream order
-//   for l: for kb: for nh: for part in {hi, lo}: one 16 KB chunk  [128 (n) x 64 (k)]
+// weight packing: fp32 nn.Linear tensors -> 16-bit (hi | lo) SW128 operand blocks in stream order
+//   forward : for l: for kb: for nh: for part: chunk [128 (n = out) x 64 (k = in)]           = W[n][k]
+//   backward: for bl: for kb: for nh: for part: chunk [128 (n = in)  x 64 (k = out)]         = W[k][n]
 // ------------------------------------------------------------------------------------------------
 struct PackParams {
   const float* w[9];   // trunk 0..7, head 0
   uint8_t* packed;
 };
 
+template <bool kF16>
 __global__ void pack_weights_kernel(PackParams pp) {
-  // chunk -> (l, kbi, nh, part)
   int chunk = blockIdx.x;
   int l = 0, base = 0;
   for (;; ++l) {
@@ -128,13 +170,40 @@ __global__ void pack_weights_kernel(PackParams pp) {
       col = kb_act_index(l, kbi) * 64 + k;
     }
     float v = col < 0 ? 0.f : W[(size_t)row * ldw + col];
-    *reinterpret_cast<uint16_t*>(dst + sw128_offset(n, k)) = split1<kFwdF16>(v, part);
+    *reinterpret_cast<uint16_t*>(dst + sw128_offset(n, k)) = split1<kF16>(v, part);
   }
 }
 
-// per-ray colour-head bias: raybias[r][n] = b8[n] + sum_k W8[n][256+k] * dir_enc(r)[k]   (fp32, exact path)
+__global__ void pack_weights_bwd_kernel(PackParams pp) {
+  int chunk = blockIdx.x;
+  int bl = 0, base = 0;
+  for (;; ++bl) {
+    int n = bwd_nkb(bl) * 2 * 2;
+    if (chunk < base + n) break;
+    base += n;
+  }
+  int rel = chunk - base;
+  int part = rel & 1, nh = (rel >> 1) & 1, kbi = rel >> 2;
+  // source layer and its row offset / leading dimension
+  const int l = bl == 0 ? 8 : (bl == 1 ? 7 : 8 - bl);
+  const int ldw = l == 4 ? 319 : (l == 8 ? 283 : 256);
+  const int rowoff = l == 7 ? 1 : 0;
+  const float* W = pp.w[l];
+  uint8_t* dst = pp.packed + (size_t)chunk * kChunkBytes;
+  for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
+    int n = e >> 6, k = e & 63;
+    int in_idx = nh * 128 + n;         // column of W (input feature of the forward layer)
+    int out_idx = kbi * 64 + k;        // row of W (output feature)
+    float v = W[(size_t)(rowoff + out_idx) * ldw + in_idx];
+    *reinterpret_cast<uint16_t*>(dst + sw128_offset(n, k)) = split1<false>(v, part);
+  }
+}
+
+// per-ray view-direction encoding (denc [R,32]) and colour-head bias
+//   raybias[r][n] = b8[n] + sum_k W8[n][256+k] * denc[r][k]   (fp32, exact path)
 __global__ void raybias_kernel(int R, const float* __restrict__ dirs, const float* __restrict__ w8,
-                               const float* __restrict__ b8, C2F c2f, float* __restrict__ raybias) {
+                               const float* __restrict__ b8, C2F c2f, float* __restrict__ raybias,
+                               float* __restrict__ denc_out) {
   __shared__ float denc[4][32];
   const int rl = threadIdx.x >> 7, n = threadIdx.x & 127;
   const int r = blockIdx.x * 4 + rl;
@@ -156,6 +225,7 @@ __global__ void raybias_kernel(int R, const float* __restrict__ dirs, const floa
       }
     }
     denc[rl][n] = val;
+    if (r < R && denc_out) denc_out[(size_t)r * 32 + n] = val;
   }
   __syncthreads();
   if (r >= R) return;
@@ -166,13 +236,102 @@ __global__ void raybias_kernel(int R, const float* __restrict__ dirs, const floa
   raybias[(size_t)r * kHW + n] = acc;
 }
 
-// ------------------------------------------------------------------------------------------------
-// the fused forward kernel
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// split 32 fp32 values of one row into hi/lo words and store them as columns [col0, col0+32) of a
+// [128 x 64] SW128 block in shared memory (and optionally in its HBM image)
+template <bool kF16>
+__device__ __forceinline__ void split_store32(const float (&f)[32], int row, int col0, uint8_t* s_hi, uint8_t* s_lo,
+                                              uint8_t* g_hi, uint8_t* g_lo) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split2<kF16>(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t off = sw128_offset(row, col0 + c * 8);
+    const uint4 vh = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+    const uint4 vl = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+    if (s_hi) {
+      *reinterpret_cast<uint4*>(s_hi + off) = vh;
+      *reinterpret_cast<uint4*>(s_lo + off) = vl;
+    }
+    if (g_hi) {
+      *reinterpret_cast<uint4*>(g_hi + off) = vh;
+      *reinterpret_cast<uint4*>(g_lo + off) = vl;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared pieces of the chain kernels
+// ------------------------------------------------------------------------------------------------
+struct ChainSmem {
+  uint8_t* base;
+  uint64_t *w_full, *w_empty, *a_ready, *d_full, *d_empty;
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem) {
+  ChainSmem s;
+  s.base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  s.w_full = bars;
+  s.w_empty = bars + kStages;
+  s.a_ready = bars + 2 * kStages;
+  s.d_full = s.a_ready + 5;
+  s.d_empty = s.d_full + 2;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  return s;
+}
+
+__device__ __forceinline__ void chain_init_barriers(const ChainSmem& s) {
+  for (int i = 0; i < kStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
+  for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps);
+  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], 1); mbar_init(&s.d_empty[i], kEpiWarps); }
+  fence_barrier_init();
+}
+
+// weight producer: one thread streams `nchunks` 16 KB chunks per tile through the ring
+__device__ __forceinline__ void chain_producer(const ChainSmem& s, const uint8_t* packed, int my_tiles, int nchunks,
+                                               bool skip_lo) {
+  uint32_t stage = 0, phase = 0;
+  for (int it = 0; it < my_tiles; ++it) {
+    for (int c = 0; c < nchunks; ++c) {
+      if (skip_lo && (c & 1)) continue;
+      mbar_wait(&s.w_empty[stage], phase ^ 1);
+      mbar_arrive_expect_tx(&s.w_full[stage], kChunkBytes);
+      bulk_g2s(s.base + kOffRing + stage * kChunkBytes, packed + (size_t)c * kChunkBytes, kChunkBytes, &s.w_full[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  }
+}
+
+// one (K block, N half): waits for its weight chunks and issues the MMAs of all passes
+__device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
+                                                  uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes) {
+  const uint32_t ring_addr = smem_u32(s.base + kOffRing);
+  for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
+    mbar_wait(&s.w_full[stage], phase);
+    tc_fence_after();
+    const uint32_t b_addr = ring_addr + stage * kChunkBytes;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t db = make_smem_desc(b_addr + ks * 32);
+      const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
+      umma_ss(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
+      if (part == 0 && passes != 1) umma_ss(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+    }
+    umma_commit(&s.w_empty[stage]);   // frees the ring slot when these MMAs have read it
+    if (++stage == kStages) { stage = 0; phase ^= 1; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused forward kernel
+// ------------------------------------------------------------------------------------------------
+template <bool kF16>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -181,13 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   float* s_w9 = reinterpret_cast<float*>(smem + kOffW9);
   float* s_misc = reinterpret_cast<float*>(smem + kOffMisc);   // [0]=b7[0], [1..3]=b9, [8..23]=c2f weights
   float* s_part = reinterpret_cast<float*>(smem + kOffPart);   // [h][row][4]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* w_full = bars;                 // [kStages]
-  uint64_t* w_empty = bars + kStages;      // [kStages]
-  uint64_t* a_ready = bars + 2 * kStages;  // [5]: act blocks 0..3, enc
-  uint64_t* d_full = a_ready + 5;          // [2]
-  uint64_t* d_empty = d_full + 2;          // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  const ChainSmem cs = chain_carve(smem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -203,85 +356,52 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
     s_misc[1] = p.b9[0]; s_misc[2] = p.b9[1]; s_misc[3] = p.b9[2];
   }
   if (tid < 16) s_misc[8 + tid] = tid < kL ? band_weight(p.c2f, kL, tid) : 0.f;
-  if (tid == 32) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 5; ++i) mbar_init(&a_ready[i], kEpiWarps);
-    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], kEpiWarps); }
-    fence_barrier_init();
-  }
+  if (tid == 32) chain_init_barriers(cs);
   if (warp == 1) {
-    tmem_alloc(s_tmem, 512);
+    tmem_alloc(cs.tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = *cs.tmem_slot;
 
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    // ============================== weight producer ==============================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int c = 0; c < kChunksPerTile; ++c) {
-          // in 1-pass mode the lo chunks (odd) are skipped
-          if (p.passes == 1 && (c & 1)) continue;
-          mbar_wait(&w_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&w_full[stage], kChunkBytes);
-          bulk_g2s(smem + kOffRing + stage * kChunkBytes, p.packed + (size_t)c * kChunkBytes, kChunkBytes, &w_full[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
+    if (lane == 0) chain_producer(cs, p.packed, my_tiles, kChunksPerTile, p.passes == 1);
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, 128, kFwdF16 ? 0 : 1);
+      const uint32_t idesc = make_idesc(128, 128, kF16 ? 0 : 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
-      const uint32_t ring_addr = smem_u32(smem + kOffRing);
       uint32_t stage = 0, phase = 0;
       uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
       uint32_t d_cnt[2] = {0, 0};
       for (int it = 0; it < my_tiles; ++it) {
         for (int l = 0; l < kNumLayers; ++l) {
           const int buf = l & 1;
-          mbar_wait(&d_empty[buf], (d_cnt[buf] & 1) ^ 1);   // epilogue of the previous user of this accumulator
+          mbar_wait(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);   // epilogue of the previous user of this accumulator
           ++d_cnt[buf];
           tc_fence_after();
           const int nkb = layer_nkb(l), nh_cnt = layer_nh(l);
           for (int kbi = 0; kbi < nkb; ++kbi) {
             uint32_t a_hi, a_lo;
             if (kb_is_enc(l, kbi)) {
-              if (l == 0) { mbar_wait(&a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
+              if (l == 0) { mbar_wait(&cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
               a_hi = enc_addr; a_lo = enc_addr + kChunkBytes;
             } else {
               int a = kb_act_index(l, kbi);
-              mbar_wait(&a_ready[a], a_cnt[a] & 1);
+              mbar_wait(&cs.a_ready[a], a_cnt[a] & 1);
               ++a_cnt[a];
               a_hi = act_addr + a * kChunkBytes; a_lo = act_addr + (4 + a) * kChunkBytes;
             }
             tc_fence_after();
-            for (int nh = 0; nh < nh_cnt; ++nh) {
-              const uint32_t d_addr = tmem_base + (uint32_t)(buf * 256 + nh * 128);
-              for (int part = 0; part < (p.passes == 1 ? 1 : 2); ++part) {
-                mbar_wait(&w_full[stage], phase);
-                tc_fence_after();
-                const uint32_t b_addr = ring_addr + stage * kChunkBytes;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t db = make_smem_desc(b_addr + ks * 32);
-                  const uint32_t first = (kbi == 0 && part == 0 && ks == 0) ? 0u : 1u;
-                  umma_ss(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, first);
-                  if (part == 0 && p.passes != 1) umma_ss(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
-                }
-                umma_commit(&w_empty[stage]);   // frees the ring slot when these MMAs have read it
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-              }
-            }
+            for (int nh = 0; nh < nh_cnt; ++nh)
+              chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
+                                kbi == 0, p.passes);
           }
-          umma_commit(&d_full[buf]);            // accumulator of layer l complete
+          umma_commit(&cs.d_full[buf]);            // accumulator of layer l complete
         }
       }
     }
@@ -320,31 +440,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
             int pr = p0 + i;
             int c = pr / kL, j = pr - c * kL;
             float arg = mul_rn(c == 0 ? x[0] : (c == 1 ? x[1] : x[2]), band_freq(j));
-            float sn, cs;
-            sincosf(arg, &sn, &cs);
+            float sn, cs_;
+            sincosf(arg, &sn, &cs_);
             float w = wts[j];
             vals[v0 + 2 * i] = mul_rn(sn, w);
-            vals[v0 + 2 * i + 1] = mul_rn(cs, w);
+            vals[v0 + 2 * i + 1] = mul_rn(cs_, w);
           }
         }
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) split2<kFwdF16>(vals[2 * i], vals[2 * i + 1], hi[i], lo[i]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t off = sw128_offset(row, h * 32 + c * 8);
-          *reinterpret_cast<uint4*>(smem + kOffEnc + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-          *reinterpret_cast<uint4*>(smem + kOffEnc + kChunkBytes + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-        }
+        split_store32<kF16>(vals, row, h * 32, smem + kOffEnc, smem + kOffEnc + kChunkBytes,
+                            p.save ? p.img.at(T_ENC, tile, 0, 0) : nullptr, p.save ? p.img.at(T_ENC, tile, 0, 1) : nullptr);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[4]);
+        if (lane == 0) mbar_arrive(&cs.a_ready[4]);
       }
 
       // ---------------- layers
       for (int l = 0; l < kNumLayers; ++l) {
         const int buf = l & 1;
-        mbar_wait(&d_full[buf], d_cnt[buf] & 1);
+        mbar_wait(&cs.d_full[buf], d_cnt[buf] & 1);
         ++d_cnt[buf];
         tc_fence_after();
         const int nchunk = l == 8 ? 2 : 4;
@@ -381,25 +494,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
               dot1 = fmaf(f[i], s_w9[128 + col0 + i], dot1);
               dot2 = fmaf(f[i], s_w9[256 + col0 + i], dot2);
             }
+            if (p.save)   // hid image for the 128->3 head's weight gradient and its ReLU mask
+              split_store32<kF16>(f, row, h * 32, nullptr, nullptr, p.img.at(T_HID, tile, j, 0), p.img.at(T_HID, tile, j, 1));
           } else {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) split2<kFwdF16>(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t off = (uint32_t)j * kChunkBytes + sw128_offset(row, h * 32 + c * 8);
-              *reinterpret_cast<uint4*>(act_hi + off) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-              *reinterpret_cast<uint4*>(act_lo + off) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-            }
+            const int tsave = l == 7 ? T_FEAT : T_H0 + l;
+            split_store32<kF16>(f, row, h * 32, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes,
+                                p.save ? p.img.at(tsave, tile, j, 0) : nullptr, p.save ? p.img.at(tsave, tile, j, 1) : nullptr);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[j]);
+            if (lane == 0) mbar_arrive(&cs.a_ready[j]);
           }
         }
         // accumulator drained: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&d_empty[buf]);
+        if (lane == 0) mbar_arrive(&cs.d_empty[buf]);
 
         if (l == 6 || l == 8) {
           // combine the two column halves of each row (warps q and q+4) through shared memory
@@ -430,6 +539,359 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// the fused input-gradient (dgrad) kernel: dL/dz chain from the colour head to layer 0
+// ------------------------------------------------------------------------------------------------
+// 32-bit mask of (hi half > 0) for columns [col0, col0+32) of one row of a saved bf16 image block
+__device__ __forceinline__ uint32_t load_relu_mask(const uint8_t* img_hi, int row, int col0) {
+  uint32_t mask = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 v = *reinterpret_cast<const uint4*>(img_hi + sw128_offset(row, col0 + c * 8));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+      uint32_t lo16 = w[i] & 0xFFFFu, hi16 = w[i] >> 16;
+      mask |= (uint32_t)((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0) << (c * 8 + 2 * i);
+      mask |= (uint32_t)((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0) << (c * 8 + 2 * i + 1);
+    }
+  }
+  return mask;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_w7r0 = reinterpret_cast<float*>(smem + kOffW7r0);
+  float* s_w9 = reinterpret_cast<float*>(smem + kOffW9);
+  const ChainSmem cs = chain_carve(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < 256; i += kThreads) s_w7r0[i] = p.w7[i];
+  for (int i = tid; i < 3 * 128; i += kThreads) s_w9[i] = p.w9[i];
+  if (tid == 32) chain_init_barriers(cs);
+  if (warp == 1) {
+    tmem_alloc(cs.tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *cs.tmem_slot;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false);
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, 128, 1);
+      const uint32_t act_addr = smem_u32(smem + kOffAct);
+      uint32_t stage = 0, phase = 0;
+      uint32_t a_cnt[4] = {0, 0, 0, 0};
+      uint32_t d_cnt[2] = {0, 0};
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int bl = 0; bl < kNumBwdLayers; ++bl) {
+          const int buf = bl & 1;
+          mbar_wait(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
+          ++d_cnt[buf];
+          tc_fence_after();
+          const int nkb = bwd_nkb(bl);
+          for (int kbi = 0; kbi < nkb; ++kbi) {
+            mbar_wait(&cs.a_ready[kbi], a_cnt[kbi] & 1);
+            ++a_cnt[kbi];
+            tc_fence_after();
+            const uint32_t a_hi = act_addr + kbi * kChunkBytes, a_lo = act_addr + (4 + kbi) * kChunkBytes;
+            for (int nh = 0; nh < 2; ++nh)
+              chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
+                                kbi == 0, 3);
+          }
+          umma_commit(&cs.d_full[buf]);
+        }
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int h = e >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    uint32_t d_cnt[2] = {0, 0};
+    uint8_t* act_hi = smem + kOffAct;
+    uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const long long m = (long long)tile * kTileM + row;
+      const bool valid = m < p.M;
+
+      // ---------------- head: g_pre = d_rgb * c (1 - c); g_raw = d_sigma * (1 - e^-sigma) [= sigmoid(z)];
+      //                  g_hid = (hid > 0) * (g_pre . W9)  -> A blocks 0, 1
+      float gp0 = 0.f, gp1 = 0.f, gp2 = 0.f, g_raw = 0.f;
+      if (valid) {
+        float c0 = p.rgb[m * 3], c1 = p.rgb[m * 3 + 1], c2 = p.rgb[m * 3 + 2];
+        gp0 = p.d_rgb[m * 3] * c0 * (1.f - c0);
+        gp1 = p.d_rgb[m * 3 + 1] * c1 * (1.f - c1);
+        gp2 = p.d_rgb[m * 3 + 2] * c2 * (1.f - c2);
+        g_raw = p.d_sigma[m] * (-expm1f(-p.sigma[m]));
+        if (h == 0) {
+          p.g_raw[m] = g_raw;
+          *reinterpret_cast<float4*>(p.g_pre + m * 4) = make_float4(gp0, gp1, gp2, 0.f);
+        }
+      }
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        const int col0 = j * 64 + h * 32;
+        const uint32_t mask = load_relu_mask(p.img.at(T_HID, tile, j, 0), row, h * 32);
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float g = fmaf(gp2, s_w9[256 + col0 + i], fmaf(gp1, s_w9[128 + col0 + i], gp0 * s_w9[col0 + i]));
+          f[i] = ((mask >> i) & 1u) ? g : 0.f;
+        }
+        split_store32<false>(f, row, h * 32, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes,
+                             p.img.at(T_GHID, tile, j, 0), p.img.at(T_GHID, tile, j, 1));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+      }
+
+      // ---------------- backward layers
+      for (int bl = 0; bl < kNumBwdLayers; ++bl) {
+        const int buf = bl & 1;
+        // ReLU mask of the forward activation this gradient flows into: feat (bl 0), h6 (bl 1), ... h0 (bl 7)
+        const int t_mask = bl == 0 ? T_FEAT : T_H0 + (7 - bl);
+        const int t_out = bl == 0 ? T_G7F : t_g(7 - bl);
+        uint32_t masks[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) masks[j] = load_relu_mask(p.img.at(t_mask, tile, j, 0), row, h * 32);
+        mbar_wait(&cs.d_full[buf], d_cnt[buf] & 1);
+        ++d_cnt[buf];
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          uint32_t v[32];
+          const int col0 = j * 64 + h * 32;
+          tmem_ld32(tmem_base + t_lane + (uint32_t)(buf * 256 + col0), v);
+          tmem_ld_wait();
+          float f[32];
+          const uint32_t mask = masks[j];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float g = __uint_as_float(v[i]);
+            if (bl == 1) g = fmaf(g_raw, s_w7r0[col0 + i], g);   // density row joins the feature gradient
+            f[i] = ((mask >> i) & 1u) ? g : 0.f;
+          }
+          const bool chain = bl != kNumBwdLayers - 1;   // G0 is only saved, nothing consumes it on-chip
+          split_store32<false>(f, row, h * 32, chain ? act_hi + (size_t)j * kChunkBytes : nullptr,
+                               chain ? act_lo + (size_t)j * kChunkBytes : nullptr, p.img.at(t_out, tile, j, 0),
+                               p.img.at(t_out, tile, j, 1));
+          if (chain) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cs.d_empty[buf]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-gradient kernel: dW[m'][n'] += sum_rows G[row][m'] * X[row][n'] over a slab of row tiles
+// ------------------------------------------------------------------------------------------------
+struct WgradJob {
+  int t_g, t_x;          // image tensors: gradient (M' side) and activation (N' side)
+  int mblk, nblk;        // 64-column blocks on each side (M' = 64 mblk in {128, 256}; N' = 64 nblk in {64, 256})
+  int tile_begin, tile_end;
+  float* dW;             // destination [*, ldw]
+  int ldw, col0;         // row stride and first column
+  int enc_cols;          // 1: N' side is the encoder block (internal column order -> reference columns)
+};
+constexpr int kWgStages = 3;
+constexpr int kWgStageBytes = 16 * 4096;   // (4 G blocks + 4 X blocks) x (hi, lo) x 32 rows x 128 B
+constexpr int kWgSmem = kWgStages * kWgStageBytes + 256;
+
+__global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const WgradJob* __restrict__ jobs, Images img) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgStages;
+  uint64_t* done = bars + 2 * kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  const WgradJob job = jobs[blockIdx.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncols = job.nblk * 64;                       // N'
+  const int mhalves = job.mblk / 2;                      // accumulators of 128 rows
+  const uint32_t tmem_cols = (mhalves * ncols <= 64) ? 64 : (mhalves * ncols <= 128 ? 128 : (mhalves * ncols <= 256 ? 256 : 512));
+
+  if (tid == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nq = (job.tile_end - job.tile_begin) * 4;    // quarter tiles (32 rows) to stream
+  const uint32_t stage_tx = (uint32_t)(job.mblk + job.nblk) * 2u * 4096u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int qi = 0; qi < nq; ++qi) {
+        const int tile = job.tile_begin + (qi >> 2), qr = qi & 3;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], stage_tx);
+        uint8_t* st = smem + stage * kWgStageBytes;
+        // stage layout: [G hi: mblk x 4 KB][G lo][X hi: nblk x 4 KB][X lo], 4 KB = rows [32 qr, 32 qr + 32) of a block
+        for (int part = 0; part < 2; ++part) {
+          for (int b = 0; b < job.mblk; ++b)
+            bulk_g2s(st + (part * 4 + b) * 4096, img.at(job.t_g, tile, b, part) + qr * 4096, 4096, &full[stage]);
+          for (int b = 0; b < job.nblk; ++b)
+            bulk_g2s(st + (8 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
+        }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, ncols, 1, 1, 1);
+      uint32_t stage = 0, phase = 0;
+      for (int qi = 0; qi < nq; ++qi) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + stage * kWgStageBytes);
+        for (int mh = 0; mh < mhalves; ++mh) {
+          const uint32_t d_addr = tmem_base + (uint32_t)(mh * ncols);
+          for (int ks = 0; ks < 2; ++ks) {   // 32 rows = 2 x K16
+            const uint64_t g_hi = make_smem_desc_mn(st + (0 + mh * 2) * 4096 + ks * 2048, 4096);
+            const uint64_t g_lo = make_smem_desc_mn(st + (4 + mh * 2) * 4096 + ks * 2048, 4096);
+            const uint64_t x_hi = make_smem_desc_mn(st + 8 * 4096 + ks * 2048, 4096);
+            const uint64_t x_lo = make_smem_desc_mn(st + 12 * 4096 + ks * 2048, 4096);
+            umma_ss(d_addr, g_hi, x_hi, idesc, (qi | ks) != 0);
+            umma_ss(d_addr, g_lo, x_hi, idesc, 1u);
+            umma_ss(d_addr, g_hi, x_lo, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    // flush warps 2..5: accumulator rows (= output features) -> atomics on dW
+    const int q = warp & 3;
+    const int rowl = q * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int mh = 0; mh < mhalves; ++mh) {
+      float* drow = job.dW + (size_t)(mh * 128 + rowl) * job.ldw + job.col0;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * ncols + c0), v);
+        tmem_ld_wait();
+        if (nq > 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            int col = c0 + i;
+            if (job.enc_cols) {
+              col = enc_ref_col(col);
+              if (col < 0) continue;
+            }
+            atomicAdd(drow + col, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core helpers on the saved images
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float img_value(const Images& img, int t, long long m, int f) {
+  const int tile = (int)(m >> 7), row = (int)(m & 127);
+  const uint32_t off = sw128_offset(row, f & 63);
+  const uint16_t hi = *reinterpret_cast<const uint16_t*>(img.at(t, tile, f >> 6, 0) + off);
+  const uint16_t lo = *reinterpret_cast<const uint16_t*>(img.at(t, tile, f >> 6, 1) + off);
+  return __uint_as_float((uint32_t)hi << 16) + __uint_as_float((uint32_t)lo << 16);
+}
+
+// out[f] += sum_m img[m][f]  (bias gradients).  One thread per feature, rows split over blockIdx.y.
+__global__ void image_colsum_kernel(Images img, int t, int nfeat, long long M, int rows_per_block, float* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nfeat) return;
+  long long m0 = (long long)blockIdx.y * rows_per_block, m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  float acc = 0.f;
+  for (long long m = m0; m < m1; ++m) acc += img_value(img, t, m, f);
+  atomicAdd(out + f, acc);
+}
+
+// dW[c][f] += sum_m g[m*gs + c] * img[m][f] ; db[c] += sum_m g[m*gs + c]     (NC narrow outputs)
+template <int NC>
+__global__ void image_narrow_wgrad_kernel(Images img, int t, int nfeat, long long M, int rows_per_block,
+                                          const float* __restrict__ g, int gs, float* __restrict__ dW, int ldw,
+                                          float* __restrict__ db) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > nfeat) return;
+  long long m0 = (long long)blockIdx.y * rows_per_block, m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  float acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+  for (long long m = m0; m < m1; ++m) {
+    const float x = f < nfeat ? img_value(img, t, m, f) : 1.f;   // feature index nfeat = the bias
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = fmaf(g[m * gs + c], x, acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (f < nfeat) atomicAdd(dW + (size_t)c * ldw + f, acc[c]);
+    else atomicAdd(db + c, acc[c]);
+  }
+}
+
+// per-ray sum of g_hid over the samples: rayS[r][n] = sum_k GHID[(r,k)][n]
+__global__ void ray_sum_ghid_kernel(Images img, int R, int S, float* __restrict__ rayS) {
+  const int n = threadIdx.x;        // 128
+  const int r = blockIdx.x;
+  float acc = 0.f;
+  for (int k = 0; k < S; ++k) acc += img_value(img, T_GHID, (long long)r * S + k, n);
+  rayS[(size_t)r * kHW + n] = acc;
+}
+
+// view-direction part of the colour head: dW8[n][256+k] += sum_r rayS[r][n] denc[r][k]
+__global__ void ray_head_wgrad_kernel(int R, int rays_per_block, const float* __restrict__ rayS,
+                                      const float* __restrict__ denc, float* __restrict__ dW8) {
+  const int n = threadIdx.x;   // 128
+  const int r0 = blockIdx.x * rays_per_block, r1 = min(R, r0 + rays_per_block);
+  float acc[kEv];
+#pragma unroll
+  for (int k = 0; k < kEv; ++k) acc[k] = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float s = rayS[(size_t)r * kHW + n];
+#pragma unroll
+    for (int k = 0; k < kEv; ++k) acc[k] = fmaf(s, denc[(size_t)r * 32 + k], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < kEv; ++k) atomicAdd(dW8 + (size_t)n * (kW + kEv) + kW + k, acc[k]);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -440,11 +902,92 @@ bool tc_supports(const SparfMLP* mlp) {
          mlp->L_xyz == kL && mlp->L_view == kLv;
 }
 
-bool tc_backward_available() { return false; }
+bool tc_backward_available() { return true; }
+
+// rays per backward chunk: <= 1024 row tiles of saved images (~2.3 GB)
+static int bwd_chunk_rays(int S) { return std::max(1, (1024 * kTileM) / S); }
+
+static size_t images_bytes(int ntiles, size_t* off) {
+  size_t total = 0;
+  for (int t = 0; t < T_COUNT; ++t) {
+    if (off) off[t] = total;
+    total += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles;
+  }
+  return total;
+}
+
+struct BwdCarve {
+  uint8_t *packed_f, *packed_b, *images;
+  float *raybias, *denc, *sigma, *rgb, *g_raw, *g_pre, *rayS;
+  WgradJob* jobs;
+  size_t total;
+};
+
+static BwdCarve bwd_carve(void* ws, int nr, int S) {
+  const size_t Mc = (size_t)nr * S;
+  const int ntiles = (int)((Mc + kTileM - 1) / kTileM);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  BwdCarve c;
+  uint8_t* b = reinterpret_cast<uint8_t*>(ws);
+  size_t o_pf = take((size_t)kChunksPerTile * kChunkBytes), o_pb = take((size_t)kBwdChunksPerTile * kChunkBytes);
+  size_t o_rb = take((size_t)nr * kHW * 4), o_de = take((size_t)nr * 32 * 4), o_si = take(Mc * 4), o_rg = take(Mc * 12);
+  size_t o_gr = take(Mc * 4), o_gp = take(Mc * 16), o_rs = take((size_t)nr * kHW * 4), o_jb = take(256 * sizeof(WgradJob));
+  size_t o_im = take(images_bytes(ntiles, nullptr));
+  c.packed_f = b + o_pf; c.packed_b = b + o_pb; c.raybias = (float*)(b + o_rb); c.denc = (float*)(b + o_de);
+  c.sigma = (float*)(b + o_si); c.rgb = (float*)(b + o_rg); c.g_raw = (float*)(b + o_gr); c.g_pre = (float*)(b + o_gp);
+  c.rayS = (float*)(b + o_rs); c.jobs = (WgradJob*)(b + o_jb); c.images = b + o_im;
+  c.total = o + 1024;
+  return c;
+}
 
 size_t tc_workspace_bytes(const SparfMLP* mlp, int R, int S, int backward, int engine) {
-  if (backward) return simt_workspace_bytes(mlp, R, S, 1);
+  if (backward) {
+    int nr = std::min(R, bwd_chunk_rays(S));
+    // ray gradients are served by the SIMT engine for now: size for whichever is larger
+    return std::max(bwd_carve(nullptr, nr, S).total, simt_workspace_bytes(mlp, R, S, 1));
+  }
   return align_up((size_t)kChunksPerTile * kChunkBytes, 256) + align_up((size_t)R * kHW * sizeof(float), 256) + 256;
+}
+
+static void fill_pack_params(const SparfMLP* mlp, PackParams& pp, uint8_t* dst) {
+  for (int l = 0; l < 8; ++l) pp.w[l] = mlp->trunk_w[l];
+  pp.w[8] = mlp->head_w[0];
+  pp.packed = dst;
+}
+
+static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int S, const float* origins, const float* dirs,
+                          const float* t, const float* noise, float* sigma, float* rgb, const uint8_t* packed,
+                          const float* raybias, const Images* img, cudaStream_t st) {
+  FwdParams p;
+  p.packed = packed;
+  p.raybias = raybias;
+  p.origins = origins; p.dirs = dirs; p.t = t; p.noise = noise;
+  p.sigma = sigma; p.rgb = rgb;
+  for (int l = 0; l < 8; ++l) p.bias[l] = mlp->trunk_b[l];
+  p.w7 = mlp->trunk_w[7];
+  p.w9 = mlp->head_w[1];
+  p.b9 = mlp->head_b[1];
+  p.c2f = C2F{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
+  p.M = (long long)nr * S;
+  p.S = S;
+  p.num_tiles = (int)((p.M + kTileM - 1) / kTileM);
+  p.passes = passes;
+  p.save = img != nullptr;
+  if (img) p.img = *img; else { p.img.base = nullptr; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem + 1024));
+    attr_set = true;
+  }
+  int grid = std::min(p.num_tiles, num_sms());
+  if (f16) tc_mlp_fwd_kernel<true><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
+  else tc_mlp_fwd_kernel<false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
+  SPARF_CHECK_LAUNCH("tc_mlp_fwd_kernel");
+  return SPARF_OK;
 }
 
 int tc_mlp_forward(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
@@ -462,50 +1005,121 @@ int tc_mlp_forward(const SparfMLP* mlp, int engine, int R, int S, const float* o
   }
   uint8_t* packed = reinterpret_cast<uint8_t*>(workspace);
   float* raybias = reinterpret_cast<float*>(packed + align_up((size_t)kChunksPerTile * kChunkBytes, 256));
-
   PackParams pp;
-  for (int l = 0; l < 8; ++l) pp.w[l] = mlp->trunk_w[l];
-  pp.w[8] = mlp->head_w[0];
-  pp.packed = packed;
-  pack_weights_kernel<<<kChunksPerTile, 256, 0, st>>>(pp);
+  fill_pack_params(mlp, pp, packed);
+  pack_weights_kernel<true><<<kChunksPerTile, 256, 0, st>>>(pp);
   SPARF_CHECK_LAUNCH("pack_weights_kernel");
-
   C2F c2f{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
-  raybias_kernel<<<ceil_div(R, 4), 512, 0, st>>>(R, dirs, mlp->head_w[0], mlp->head_b[0], c2f, raybias);
+  raybias_kernel<<<ceil_div(R, 4), 512, 0, st>>>(R, dirs, mlp->head_w[0], mlp->head_b[0], c2f, raybias, nullptr);
   SPARF_CHECK_LAUNCH("raybias_kernel");
-
-  FwdParams p;
-  p.packed = packed;
-  p.raybias = raybias;
-  p.origins = origins; p.dirs = dirs; p.t = t; p.noise = noise;
-  p.sigma = sigma; p.rgb = rgb;
-  for (int l = 0; l < 8; ++l) p.bias[l] = mlp->trunk_b[l];
-  p.w7 = mlp->trunk_w[7];
-  p.w9 = mlp->head_w[1];
-  p.b9 = mlp->head_b[1];
-  p.c2f = c2f;
-  p.M = (long long)R * S;
-  p.S = S;
-  p.num_tiles = (int)((p.M + kTileM - 1) / kTileM);
-  p.passes = engine == SPARF_ENGINE_TC_1X ? 1 : 3;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
-    attr_set = true;
-  }
-  int grid = std::min(p.num_tiles, num_sms());
-  tc_mlp_fwd_kernel<<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
-  SPARF_CHECK_LAUNCH("tc_mlp_fwd_kernel");
-  return SPARF_OK;
+  return launch_forward(mlp, true, engine == SPARF_ENGINE_TC_1X ? 1 : 3, R, S, origins, dirs, t, noise, sigma, rgb, packed,
+                        raybias, nullptr, st);
 }
 
 int tc_mlp_backward(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
                     const float* t, const float* noise, const float* d_sigma, const float* d_rgb,
                     const SparfMLPGrad* grad, float* d_origins, float* d_dirs, void* workspace,
                     size_t workspace_bytes, cudaStream_t st) {
-  // until the tcgen05 dgrad / wgrad kernels land, gradients come from the fp32 SIMT engine
-  return simt_mlp_backward(mlp, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace,
-                           workspace_bytes, st);
+  int rc = simt_validate(mlp);
+  if (rc) return rc;
+  if (d_origins != nullptr || d_dirs != nullptr) {
+    // gradients w.r.t. the rays (camera-pose optimisation) are served by the fp32 SIMT engine
+    return simt_mlp_backward(mlp, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace,
+                             workspace_bytes, st);
+  }
+  if (!tc_supports(mlp)) {
+    set_error("tcgen05 engine: unsupported MLP shape");
+    return SPARF_ERR_UNSUPPORTED;
+  }
+  if (workspace_bytes < tc_workspace_bytes(mlp, R, S, 1, engine)) {
+    set_error("tc_mlp_backward: workspace %zu < %zu bytes", workspace_bytes, tc_workspace_bytes(mlp, R, S, 1, engine));
+    return SPARF_ERR_WORKSPACE;
+  }
+  const int nrc = std::min(R, bwd_chunk_rays(S));
+  const C2F c2f{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
+  for (int r0 = 0; r0 < R; r0 += nrc) {
+    const int nr = std::min(nrc, R - r0);
+    const long long Mc = (long long)nr * S;
+    const size_t m0 = (size_t)r0 * S;
+    const int ntiles = (int)((Mc + kTileM - 1) / kTileM);
+    BwdCarve c = bwd_carve(workspace, nr, S);
+    Images img;
+    img.base = c.images;
+    images_bytes(ntiles, img.off);
+
+    PackParams pp;
+    fill_pack_params(mlp, pp, c.packed_f);
+    pack_weights_kernel<false><<<kChunksPerTile, 256, 0, st>>>(pp);
+    SPARF_CHECK_LAUNCH("pack_weights_kernel<bf16>");
+    fill_pack_params(mlp, pp, c.packed_b);
+    pack_weights_bwd_kernel<<<kBwdChunksPerTile, 256, 0, st>>>(pp);
+    SPARF_CHECK_LAUNCH("pack_weights_bwd_kernel");
+    raybias_kernel<<<ceil_div(nr, 4), 512, 0, st>>>(nr, dirs + (size_t)r0 * 3, mlp->head_w[0], mlp->head_b[0], c2f, c.raybias, c.denc);
+    SPARF_CHECK_LAUNCH("raybias_kernel");
+
+    // 1. forward re-run (bf16 halves) dumping the operand images
+    rc = launch_forward(mlp, false, 3, nr, S, origins + (size_t)r0 * 3, dirs + (size_t)r0 * 3, t + m0,
+                        noise ? noise + m0 : nullptr, c.sigma, c.rgb, c.packed_f, c.raybias, &img, st);
+    if (rc) return rc;
+
+    // 2. input-gradient chain
+    BwdParams bp;
+    bp.packed = c.packed_b;
+    bp.d_sigma = d_sigma + m0; bp.d_rgb = d_rgb + m0 * 3;
+    bp.sigma = c.sigma; bp.rgb = c.rgb;
+    bp.g_raw = c.g_raw; bp.g_pre = c.g_pre;
+    bp.w7 = mlp->trunk_w[7]; bp.w9 = mlp->head_w[1];
+    bp.M = Mc; bp.num_tiles = ntiles; bp.img = img;
+    tc_mlp_dgrad_kernel<<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
+    SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
+
+    // 3. weight gradients: job table = (layer, slab of row tiles), ~one CTA per SM
+    WgradJob jobs[256];
+    int nj = 0;
+    auto add_jobs = [&](int tg, int tx, int mblk, int nblk, float* dW, int ldw, int col0, int enc, int slabs) {
+      slabs = std::max(1, std::min(slabs, ntiles));
+      for (int s = 0; s < slabs; ++s) {
+        WgradJob j;
+        j.t_g = tg; j.t_x = tx; j.mblk = mblk; j.nblk = nblk;
+        j.tile_begin = (int)((long long)ntiles * s / slabs);
+        j.tile_end = (int)((long long)ntiles * (s + 1) / slabs);
+        j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc;
+        jobs[nj++] = j;
+      }
+    };
+    add_jobs(T_GHID, T_FEAT, 2, 4, grad->head_w[0], kW + kEv, 0, 0, 9);                       // head 0, feature part
+    add_jobs(T_G7F, T_H0 + 6, 4, 4, grad->trunk_w[7] + kW, kW, 0, 0, 17);                      // trunk 7 rows 1..256
+    for (int l = 6; l >= 1; --l)
+      add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 17);
+    add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 5);                        // skip part of layer 4
+    add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 5);                              // layer 0
+    SPARF_CHECK_CUDA(cudaMemcpyAsync(c.jobs, jobs, sizeof(WgradJob) * nj, cudaMemcpyHostToDevice, st));
+    tc_mlp_wgrad_kernel<<<nj, 192, kWgSmem + 1024, st>>>(c.jobs, img);
+    SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
+
+    // 4. CUDA-core leftovers: biases, density row, 128->3 head, view-direction columns
+    const int rpb = 2048;
+    const int nby = ceil_div(Mc, rpb);
+    image_colsum_kernel<<<dim3(1, nby), 128, 0, st>>>(img, T_GHID, kHW, Mc, rpb, grad->head_b[0]);
+    SPARF_CHECK_LAUNCH("image_colsum_kernel(head)");
+    image_colsum_kernel<<<dim3(1, nby), 256, 0, st>>>(img, T_G7F, kW, Mc, rpb, grad->trunk_b[7] + 1);
+    SPARF_CHECK_LAUNCH("image_colsum_kernel(trunk7)");
+    for (int l = 6; l >= 0; --l) {
+      image_colsum_kernel<<<dim3(1, nby), 256, 0, st>>>(img, t_g(l), kW, Mc, rpb, grad->trunk_b[l]);
+      SPARF_CHECK_LAUNCH("image_colsum_kernel(trunk)");
+    }
+    image_narrow_wgrad_kernel<1><<<dim3(ceil_div(kW + 1, 128), nby), 128, 0, st>>>(img, T_H0 + 6, kW, Mc, rpb, c.g_raw, 1,
+                                                                                  grad->trunk_w[7], kW, grad->trunk_b[7]);
+    SPARF_CHECK_LAUNCH("image_narrow_wgrad_kernel<1>");
+    image_narrow_wgrad_kernel<3><<<dim3(ceil_div(kHW + 1, 128), nby), 128, 0, st>>>(img, T_HID, kHW, Mc, rpb, c.g_pre, 4,
+                                                                                   grad->head_w[1], kHW, grad->head_b[1]);
+    SPARF_CHECK_LAUNCH("image_narrow_wgrad_kernel<3>");
+    ray_sum_ghid_kernel<<<nr, 128, 0, st>>>(img, nr, S, c.rayS);
+    SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
+    ray_head_wgrad_kernel<<<ceil_div(nr, 64), 128, 0, st>>>(nr, 64, c.rayS, c.denc, grad->head_w[0]);
+    SPARF_CHECK_LAUNCH("ray_head_wgrad_kernel");
+  }
+  return SPARF_OK;
 }
 
 }  // namespace sparf
