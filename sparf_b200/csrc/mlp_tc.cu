@@ -833,36 +833,93 @@ __device__ __forceinline__ float img_value(const Images& img, int t, long long m
   return __uint_as_float((uint32_t)hi << 16) + __uint_as_float((uint32_t)lo << 16);
 }
 
-// out[f] += sum_m img[m][f]  (bias gradients).  One thread per feature, rows split over blockIdx.y.
-__global__ void image_colsum_kernel(Images img, int t, int nfeat, long long M, int rows_per_block, float* __restrict__ out) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= nfeat) return;
-  long long m0 = (long long)blockIdx.y * rows_per_block, m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
-  float acc = 0.f;
-  for (long long m = m0; m < m1; ++m) acc += img_value(img, t, m, f);
-  atomicAdd(out + f, acc);
+// One launch for every row-reduction over the saved images (bias gradients and the two narrow layers):
+//   mode 0:  out[f]            += sum_m img[m][f]                                   (colsum -> bias grads)
+//   mode 1/3: out[c*ldo + f]   += sum_m g[m*gs + c] * img[m][f], out_bias[c] += sum_m g[m*gs + c]
+// Block = 256 threads = 8 row groups x 32 sixteen-byte chunks (8 features each); a block owns a few row
+// tiles, reads them with 16-byte loads along the swizzled rows, reduces in shared memory, one atomic per
+// feature per block.
+struct ReduceJob {
+  int t, nblk, nc;     // image tensor, 64-feature blocks (2 or 4), nc = 0 (colsum), 1 or 3 (narrow outputs)
+  const float* g;
+  int gs;
+  float* out;
+  int ldo;
+  float* out_bias;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&x)[8]) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    x[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+  }
 }
 
-// dW[c][f] += sum_m g[m*gs + c] * img[m][f] ; db[c] += sum_m g[m*gs + c]     (NC narrow outputs)
-template <int NC>
-__global__ void image_narrow_wgrad_kernel(Images img, int t, int nfeat, long long M, int rows_per_block,
-                                          const float* __restrict__ g, int gs, float* __restrict__ dW, int ldw,
-                                          float* __restrict__ db) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f > nfeat) return;
-  long long m0 = (long long)blockIdx.y * rows_per_block, m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
-  float acc[NC];
+__global__ void __launch_bounds__(256) image_reduce_kernel(const ReduceJob* __restrict__ jobs, Images img, long long M,
+                                                           int ntiles, int tiles_per_block) {
+  __shared__ float red[8][32][25];
+  const ReduceJob job = jobs[blockIdx.y];
+  const int tid = threadIdx.x, c16 = tid & 31, rg = tid >> 5;
+  const int fb = c16 >> 3, c = c16 & 7;
+  const bool active = fb < job.nblk;
+  const int nc = job.nc;
+  float acc[24];
 #pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = 0.f;
-  for (long long m = m0; m < m1; ++m) {
-    const float x = f < nfeat ? img_value(img, t, m, f) : 1.f;   // feature index nfeat = the bias
+  for (int i = 0; i < 24; ++i) acc[i] = 0.f;
+  float accb[3] = {0.f, 0.f, 0.f};
+  const int t0 = blockIdx.x * tiles_per_block, t1 = min(ntiles, t0 + tiles_per_block);
+  for (int tile = t0; tile < t1; ++tile) {
+    const uint8_t* bh = img.at(job.t, tile, active ? fb : 0, 0);
+    const uint8_t* bl = img.at(job.t, tile, active ? fb : 0, 1);
+    for (int row = rg; row < 128; row += 8) {
+      const long long m = (long long)tile * 128 + row;
+      if (m >= M) break;
+      if (!active) continue;
+      const uint32_t off = sw128_offset(row, c * 8);
+      float x[8];
+      unpack8(*reinterpret_cast<const uint4*>(bh + off), *reinterpret_cast<const uint4*>(bl + off), x);
+      if (nc == 0) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] = fmaf(g[m * gs + c], x, acc[c]);
+        for (int i = 0; i < 8; ++i) acc[i] += x[i];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (k < nc) {
+            const float gv = job.g[m * job.gs + k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[k * 8 + i] = fmaf(gv, x[i], acc[k * 8 + i]);
+            if (c16 == 0) accb[k] += gv;
+          }
+        }
+      }
+    }
   }
+  const int nk = nc == 0 ? 1 : nc;
+  for (int k = 0; k < nk; ++k)
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    if (f < nfeat) atomicAdd(dW + (size_t)c * ldw + f, acc[c]);
-    else atomicAdd(db + c, acc[c]);
+    for (int i = 0; i < 8; ++i) red[rg][c16][k * 8 + i] = acc[k * 8 + i];
+  if (c16 == 0) red[rg][0][24] = 0.f;
+  __syncthreads();
+  // 256 threads: thread -> (feature chunk c16', element i) for k = 0.. ; sum over the 8 row groups
+  for (int idx = tid; idx < 32 * 8 * nk; idx += 256) {
+    const int k = idx / 256, rem = idx % 256, cc = rem >> 3, i = rem & 7;
+    if ((cc >> 3) >= job.nblk) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v += red[r][cc][k * 8 + i];
+    atomicAdd(job.out + (size_t)k * job.ldo + cc * 8 + i, v);
+  }
+  if (nc > 0 && job.out_bias) {
+    __syncthreads();
+    if (c16 == 0) { red[rg][0][0] = accb[0]; red[rg][0][1] = accb[1]; red[rg][0][2] = accb[2]; }
+    __syncthreads();
+    if (tid < nc) {
+      float v = 0.f;
+      for (int r = 0; r < 8; ++r) v += red[r][0][tid];
+      atomicAdd(job.out_bias + tid, v);
+    }
   }
 }
 
@@ -920,6 +977,7 @@ struct BwdCarve {
   uint8_t *packed_f, *packed_b, *images;
   float *raybias, *denc, *sigma, *rgb, *g_raw, *g_pre, *rayS;
   WgradJob* jobs;
+  ReduceJob* rjobs;
   size_t total;
 };
 
@@ -933,10 +991,11 @@ static BwdCarve bwd_carve(void* ws, int nr, int S) {
   size_t o_pf = take((size_t)kChunksPerTile * kChunkBytes), o_pb = take((size_t)kBwdChunksPerTile * kChunkBytes);
   size_t o_rb = take((size_t)nr * kHW * 4), o_de = take((size_t)nr * 32 * 4), o_si = take(Mc * 4), o_rg = take(Mc * 12);
   size_t o_gr = take(Mc * 4), o_gp = take(Mc * 16), o_rs = take((size_t)nr * kHW * 4), o_jb = take(256 * sizeof(WgradJob));
+  size_t o_rj = take(16 * sizeof(ReduceJob));
   size_t o_im = take(images_bytes(ntiles, nullptr));
   c.packed_f = b + o_pf; c.packed_b = b + o_pb; c.raybias = (float*)(b + o_rb); c.denc = (float*)(b + o_de);
   c.sigma = (float*)(b + o_si); c.rgb = (float*)(b + o_rg); c.g_raw = (float*)(b + o_gr); c.g_pre = (float*)(b + o_gp);
-  c.rayS = (float*)(b + o_rs); c.jobs = (WgradJob*)(b + o_jb); c.images = b + o_im;
+  c.rayS = (float*)(b + o_rs); c.jobs = (WgradJob*)(b + o_jb); c.rjobs = (ReduceJob*)(b + o_rj); c.images = b + o_im;
   c.total = o + 1024;
   return c;
 }
@@ -1098,22 +1157,21 @@ int tc_mlp_backward(const SparfMLP* mlp, int engine, int R, int S, const float* 
     SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
 
     // 4. CUDA-core leftovers: biases, density row, 128->3 head, view-direction columns
-    const int rpb = 2048;
-    const int nby = ceil_div(Mc, rpb);
-    image_colsum_kernel<<<dim3(1, nby), 128, 0, st>>>(img, T_GHID, kHW, Mc, rpb, grad->head_b[0]);
-    SPARF_CHECK_LAUNCH("image_colsum_kernel(head)");
-    image_colsum_kernel<<<dim3(1, nby), 256, 0, st>>>(img, T_G7F, kW, Mc, rpb, grad->trunk_b[7] + 1);
-    SPARF_CHECK_LAUNCH("image_colsum_kernel(trunk7)");
-    for (int l = 6; l >= 0; --l) {
-      image_colsum_kernel<<<dim3(1, nby), 256, 0, st>>>(img, t_g(l), kW, Mc, rpb, grad->trunk_b[l]);
-      SPARF_CHECK_LAUNCH("image_colsum_kernel(trunk)");
-    }
-    image_narrow_wgrad_kernel<1><<<dim3(ceil_div(kW + 1, 128), nby), 128, 0, st>>>(img, T_H0 + 6, kW, Mc, rpb, c.g_raw, 1,
-                                                                                  grad->trunk_w[7], kW, grad->trunk_b[7]);
-    SPARF_CHECK_LAUNCH("image_narrow_wgrad_kernel<1>");
-    image_narrow_wgrad_kernel<3><<<dim3(ceil_div(kHW + 1, 128), nby), 128, 0, st>>>(img, T_HID, kHW, Mc, rpb, c.g_pre, 4,
-                                                                                   grad->head_w[1], kHW, grad->head_b[1]);
-    SPARF_CHECK_LAUNCH("image_narrow_wgrad_kernel<3>");
+    ReduceJob rj[16];
+    int nrj = 0;
+    auto add_red = [&](int t, int nblk, int nc, const float* g, int gs, float* out, int ldo, float* ob) {
+      ReduceJob j; j.t = t; j.nblk = nblk; j.nc = nc; j.g = g; j.gs = gs; j.out = out; j.ldo = ldo; j.out_bias = ob;
+      rj[nrj++] = j;
+    };
+    add_red(T_GHID, 2, 0, nullptr, 0, grad->head_b[0], 0, nullptr);
+    add_red(T_G7F, 4, 0, nullptr, 0, grad->trunk_b[7] + 1, 0, nullptr);
+    for (int l = 6; l >= 0; --l) add_red(t_g(l), 4, 0, nullptr, 0, grad->trunk_b[l], 0, nullptr);
+    add_red(T_H0 + 6, 4, 1, c.g_raw, 1, grad->trunk_w[7], kW, grad->trunk_b[7]);        // density row of trunk 7
+    add_red(T_HID, 2, 3, c.g_pre, 4, grad->head_w[1], kHW, grad->head_b[1]);             // 128 -> 3 colour layer
+    SPARF_CHECK_CUDA(cudaMemcpyAsync(c.rjobs, rj, sizeof(ReduceJob) * nrj, cudaMemcpyHostToDevice, st));
+    const int tpb = 4;
+    image_reduce_kernel<<<dim3(ceil_div(ntiles, tpb), nrj), 256, 0, st>>>(c.rjobs, img, Mc, ntiles, tpb);
+    SPARF_CHECK_LAUNCH("image_reduce_kernel");
     ray_sum_ghid_kernel<<<nr, 128, 0, st>>>(img, nr, S, c.rayS);
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
     ray_head_wgrad_kernel<<<ceil_div(nr, 64), 128, 0, st>>>(nr, 64, c.rayS, c.denc, grad->head_w[0]);

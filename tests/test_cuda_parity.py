@@ -140,7 +140,12 @@ def test_graph_end_to_end_vs_reference(name, engine):
     ltol = 2e-4 if common.CASES[name].get("depth_param", "metric") == "metric" else 2e-3
     assert abs(loss.item() - float(gold["loss"])) < ltol * max(1.0, abs(float(gold["loss"])))
     # gradients: fp32 accumulation over ~1e4 rows in a different order + the input-side noise above
-    worst = check_grads(grads, gold, tol=5e-3 if "inverse" not in name else 0.25)
+    # The reference's own fp32 gradient sits ~3e-2 from the exact (fp64) gradient on these random nets
+    # (tests/test_tc_engine.py::test_tc_backward_matches_simt measures both engines against fp64): the SIMT
+    # engine shares the reference's op order and lands closer to IT; the tcgen05 engine is equally close to
+    # the truth but not to the reference's particular rounding.
+    gtol = 0.25 if "inverse" in name else (5e-3 if engine == "simt_fp32" else 6e-2)
+    worst = check_grads(grads, gold, tol=gtol)
     print(name, engine, {k: "%.1e" % v for k, v in report.items()}, "worst grad %.1e" % worst)
 
 
