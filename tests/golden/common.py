@@ -65,8 +65,22 @@ def make_opt(*, S=128, S_fine=128, fine=False, depth_param="metric", depth_range
     opt.huber_loss_for_photometric = True
     opt.start_iter = edict(photometric=0, corres=0, depth_cons=0)
     opt.loss_weight = edict(parametrization="exp", equalize_losses=False, render=0, fg_mask=None,
-                            distortion=None, depth_patch=None, corres=None, depth_cons=None)
+                            distortion=None, depth_patch=None, corres=None, depth_cons=None,
+                            render_matches=None)
     opt.depth_regu_patch_size = 2
+    # loss-layer options (train_settings/default_config.py:130-202)
+    opt.precrop_frac, opt.precrop_iters, opt.sampled_fraction_in_center = 0.5, 0, 0.0
+    opt.start_ratio = edict(photometric=None, corres=None, depth_cons=None)
+    opt.gradually_decrease_corres_weight = False
+    opt.ratio_start_decrease_corres_weight = None
+    opt.iter_start_decrease_corres_weight = 0
+    opt.corres_weight_reduct_at_x_iter = 10000
+    opt.gradually_decrease_depth_cons_loss = False
+    opt.depth_cons_loss_reduct_at_x_iter = 10000
+    opt.use_homography_flow = False
+    opt.min_nbr_matches = 500
+    opt.matching_pair_generation = "all_to_all"
+    opt.loss_type = "photometric"
     return opt
 
 
@@ -176,6 +190,62 @@ def subsample(x, n=257):
         return flat.copy()
     step = max(1, flat.size // n)
     return flat[::step].copy()
+
+
+class FakeFlowNet:
+    """Stand-in for source/models/flow_net.FlowSelectionWrapper (PDC-Net needs a checkpoint we do not have):
+    deterministic synthetic correspondence + confidence maps with the duck type the correspondence loss uses
+    (SURVEY.md §8b): `.combi_list`, `.compute_flow_and_confidence_map_of_combi_list`, `.visualize_mapping_combinations`."""
+
+    def __init__(self, n_views, H, W):
+        self.H, self.W = H, W
+        pairs = [[i, j] for i in range(n_views) for j in range(n_views) if i != j]
+        self.combi_list = torch.tensor(pairs).T            # 2 x N (target, source)
+
+    def compute_flow_and_confidence_map_of_combi_list(self, images, combi_list_tar_src, plot=False, use_homography=False):
+        H, W = self.H, self.W
+        N = combi_list_tar_src.shape[1]
+        yy, xx = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+        maps, confs = [], []
+        for k in range(N):
+            dx, dy = 1.5 + 0.25 * k, -0.75 + 0.2 * k
+            maps.append(torch.stack([xx + dx + 0.02 * yy, yy + dy - 0.01 * xx], 0))
+            conf = torch.full((1, H, W), 0.99)
+            conf[:, :2] = 0.5
+            conf[:, :, -3:] = 0.6
+            confs.append(conf - 0.0005 * k)
+        dev = images.device
+        return torch.stack(maps).to(dev), torch.stack(confs).to(dev), None
+
+    def visualize_mapping_combinations(self, **kw):
+        return np.zeros((self.H, self.W, 3), np.uint8)
+
+
+LOSS_CASES = {
+    # BASELINE configs 3/4 flavour: joint pose + NeRF, photometric + correspondence + depth-consistency,
+    # hierarchical sampling, BARF c2f mid-schedule, stratified jitter
+    "c7_sparf_losses": dict(seed=7, B=3, H=24, W=32, n_rays=32, S=32, S_fine=32, fine=True, barf_c2f=(0.4, 0.7),
+                            progress=0.5, depth_range=(1.2, 5.2), peaky=True, sigma_bias=-2.0, stratified=True,
+                            rand_rays=96, min_nbr_matches=50, iteration=10),
+}
+
+
+def loss_case_inputs(name):
+    c = dict(LOSS_CASES[name])
+    opt = make_opt(S=c["S"], S_fine=c["S_fine"], fine=c["fine"], depth_range=c["depth_range"], stratified=c["stratified"],
+                   barf_c2f=c["barf_c2f"], rand_rays=c["rand_rays"])
+    opt.loss_type = "photometric_and_corres_and_depth_cons"
+    opt.loss_weight.corres = -3.0
+    opt.loss_weight.depth_cons = -3.0
+    opt.min_nbr_matches = c["min_nbr_matches"]
+    data = make_scene(c["seed"], c["B"], c["H"], c["W"])
+    data.depth_range = torch.tensor([list(map(float, c["depth_range"]))] * c["B"])
+    rng = np.random.default_rng(c["seed"] + 3000)
+    ray_idx = torch.from_numpy(rng.permutation(c["H"] * c["W"])[: c["n_rays"]].astype(np.int64))
+    sd = det_weights(opt, c["seed"], peaky=c["peaky"], progress=c["progress"], sigma_bias=c["sigma_bias"])
+    sd_fine = det_weights(opt, c["seed"] + 77, peaky=c["peaky"], progress=c["progress"], sigma_bias=c["sigma_bias"])
+    init_w2c = perturb_poses(data.pose, c["seed"], sigma=0.02)
+    return c, opt, data, ray_idx, sd, sd_fine, init_w2c
 
 
 # --------------------------------------------------------------------------------------

@@ -54,13 +54,19 @@ class RandomRecorder:
         self.randn_calls.append(x.clone())
         return x
 
+    def randperm(self, n, device=None, **kw):
+        x = torch.from_numpy(self.rng.permutation(int(n)).astype(np.int64))
+        self.randperm_calls.append(x.clone())
+        return x
+
     def __enter__(self):
-        self._rand, self._randn_like = torch.rand, torch.randn_like
-        torch.rand, torch.randn_like = self.rand, self.randn_like
+        self.randperm_calls = []
+        self._rand, self._randn_like, self._randperm = torch.rand, torch.randn_like, torch.randperm
+        torch.rand, torch.randn_like, torch.randperm = self.rand, self.randn_like, self.randperm
         return self
 
     def __exit__(self, *a):
-        torch.rand, torch.randn_like = self._rand, self._randn_like
+        torch.rand, torch.randn_like, torch.randperm = self._rand, self._randn_like, self._randperm
 
 
 class PoseGraph(ref_renderer.Graph):
@@ -151,7 +157,68 @@ def run_case(name):
     print("%-20s loss=%.8f  keys=%d  %.1f KB" % (name, loss.item(), len(out_npz), os.path.getsize(path) / 1024))
 
 
+def run_loss_case(name):
+    """Full SPARF step (photometric + correspondence + depth-consistency) through the reference's own loss
+    modules (source/training/core/{base_losses,corres_loss,depth_cons_loss,loss_factory}.py)."""
+    from unittest.mock import MagicMock
+    import torchvision  # noqa: F401  (must be imported before the mocks)
+    for m in ["imageio", "matplotlib", "matplotlib.pyplot", "matplotlib.backends", "matplotlib.backends.backend_agg",
+              "matplotlib.figure", "matplotlib.cm", "mpl_toolkits", "mpl_toolkits.mplot3d", "mpl_toolkits.mplot3d.art3d",
+              "coloredlogs", "source.models.flow_net", "source.utils.colmap_initialization.sfm",
+              "source.utils.colmap_initialization.triangulation_w_known_poses",
+              "third_party.DenseMatching.utils_flow.pixel_wise_mapping"]:
+        sys.modules.setdefault(m, MagicMock())
+    from source.training.core.loss_factory import define_loss
+    from easydict import EasyDict as edict
+
+    c, opt, data, ray_idx, sd, sd_fine, init_w2c = common.loss_case_inputs(name)
+    dev = torch.device("cpu")
+    pose_net = FirstTwoColunmnsPoseParameters(opt, nbr_poses=c["B"], initial_poses_w2c=init_w2c, device=dev)
+    net = PoseGraph(opt, dev, pose_net)
+    net.nerf.load_state_dict(sd)
+    net.nerf_fine.load_state_dict(sd_fine)
+    net.train()
+    train_data = edict(all=data)
+    train_data.__class__.__len__ = lambda self: c["B"]
+    flow = common.FakeFlowNet(c["B"], c["H"], c["W"])
+    np.random.seed(c["seed"])
+    with RandomRecorder(c["seed"]) as rec:
+        loss_module = define_loss(opt.loss_type, opt, net, train_data, dev, flow_net=flow)
+        data["iter"] = c["iteration"]
+        out = net.render_image_at_specific_rays(opt, data, iter=c["iteration"], ray_idx=ray_idx, mode="train")
+        data.poses_w2c = net.get_w2c_pose(opt, data, mode="train")
+        loss_dict, stats, _ = loss_module.compute_loss(opt, data, out, iteration=c["iteration"], mode="train")
+    loss_dict["all"].backward()
+    out_npz = {"loss_" + k: np.float64(v.item()) for k, v in loss_dict.items() if torch.is_tensor(v) and v.dim() == 0}
+    for i, r in enumerate(rec.rand_calls):
+        out_npz["rand_%d" % i] = r.numpy()
+    for i, r in enumerate(rec.randperm_calls):
+        out_npz["randperm_%d" % i] = r.numpy()
+    for tag, m in (("nerf", net.nerf), ("nerf_fine", net.nerf_fine)):
+        for pname, p in m.named_parameters():
+            if pname == "progress":
+                continue
+            g = p.grad.numpy()
+            key = "grad_%s.%s" % (tag, pname)
+            if pname.endswith("bias"):
+                out_npz[key] = g
+            else:
+                out_npz[key + ".sub"] = common.subsample(g)
+                out_npz[key + ".sum"] = np.float64(g.astype(np.float64).sum())
+                out_npz[key + ".sumsq"] = np.float64((g.astype(np.float64) ** 2).sum())
+    out_npz["grad_pose_embedding"] = net.pose_net.pose_embedding.grad.numpy()
+    out_npz["out_rgb"] = out["rgb"].detach().numpy()
+    out_npz["out_depth_fine"] = out["depth_fine"].detach().numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out_npz)
+    print("%-20s %s  %.1f KB" % (name, {k: round(float(v), 6) for k, v in out_npz.items() if k.startswith("loss_")},
+                                  os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(common.CASES)
+    names = sys.argv[1:] or (list(common.CASES) + list(common.LOSS_CASES))
     for n in names:
-        run_case(n)
+        if n in common.LOSS_CASES:
+            run_loss_case(n)
+        else:
+            run_case(n)

@@ -113,6 +113,10 @@ class RandomReplayer:
     def __init__(self, gold):
         self.rand = [torch.from_numpy(gold[k]) for k in sorted(k for k in gold if k.startswith("rand_"))]
         self.randn = [torch.from_numpy(gold[k]) for k in sorted(k for k in gold if k.startswith("randn_"))]
+        key = lambda k: int(k.split("_")[1])
+        self.rand = [torch.from_numpy(gold[k]) for k in sorted((k for k in gold if k.startswith("rand_")), key=key)]
+        self.randn = [torch.from_numpy(gold[k]) for k in sorted((k for k in gold if k.startswith("randn_")), key=key)]
+        self.perm = [torch.from_numpy(gold[k]) for k in sorted((k for k in gold if k.startswith("randperm_")), key=key)]
 
     def _rand(self, *shape, device=None, **kw):
         x = self.rand.pop(0)
@@ -121,13 +125,18 @@ class RandomReplayer:
     def _randn_like(self, t, **kw):
         return self.randn.pop(0).to(t.device)
 
+    def _randperm(self, n, device=None, **kw):
+        x = self.perm.pop(0)
+        assert x.numel() == int(n), (x.numel(), n)
+        return x.to(device) if device is not None else x
+
     def __enter__(self):
-        self._o = (torch.rand, torch.randn_like)
-        torch.rand, torch.randn_like = self._rand, self._randn_like
+        self._o = (torch.rand, torch.randn_like, torch.randperm)
+        torch.rand, torch.randn_like, torch.randperm = self._rand, self._randn_like, self._randperm
         return self
 
     def __exit__(self, *a):
-        torch.rand, torch.randn_like = self._o
+        torch.rand, torch.randn_like, torch.randperm = self._o
 
 
 def build_graph(name, device="cuda"):
