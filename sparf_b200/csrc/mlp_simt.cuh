@@ -20,5 +20,8 @@ int simt_mlp_backward(const SparfMLP* mlp, int R, int S, const float* origins, c
 
 // shared small kernels reused by the tensor-core engine
 __global__ void c2f_weights_kernel(C2F c, int L_xyz, int L_view, float* __restrict__ wts);
+// view-direction encoding backward (d denc -> d dirs through unit = d/|d|), denc/Gdenc rows of Evp floats
+__global__ void direnc_bwd_kernel(int nrays, int L, int Evp, const float* __restrict__ denc, const float* __restrict__ Gdenc,
+                                  const float* __restrict__ dirs, float* __restrict__ d_d);
 
 }  // namespace sparf

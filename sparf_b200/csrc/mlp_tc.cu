@@ -949,6 +949,209 @@ __global__ void ray_head_wgrad_kernel(int R, int rays_per_block, const float* __
   for (int k = 0; k < kEv; ++k) atomicAdd(dW8 + (size_t)n * (kW + kEv) + kW + k, acc[k]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// ray gradients (camera-pose optimisation): dL/d enc = G4 . W4[:, 256:319] + G0 . W0 on tensor cores, then the
+// positional-encoding backward and the reduction over each ray's samples in the epilogue.
+//   d/dx [w sin(f x)] = f * (w cos(f x)) = f * enc_cos ;  d/dx [w cos(f x)] = -f * enc_sin
+// ------------------------------------------------------------------------------------------------
+constexpr int kEgStages = 3;
+constexpr int kEgWBytes = 16 * 8192;                         // 2 layers x 4 K blocks x (hi, lo) x [64 x 64]
+constexpr int kEgStageBytes = 2 * kChunkBytes;               // one K block of G: hi + lo
+constexpr int kEgSmem = kEgWBytes + kEgStages * kEgStageBytes + 256;
+
+// chunk (li in {0: layer 4 skip columns, 1: layer 0}, kb, part): [64 (n = internal encoder column) x 64 (k = out feature)]
+__global__ void pack_weights_enc_kernel(const float* __restrict__ w4, const float* __restrict__ w0, uint8_t* __restrict__ packed) {
+  const int chunk = blockIdx.x;              // (li * 4 + kb) * 2 + part
+  const int part = chunk & 1, kb = (chunk >> 1) & 3, li = chunk >> 3;
+  const float* W = li == 0 ? w4 : w0;
+  const int ldw = li == 0 ? kW + 63 : 63, colbase = li == 0 ? kW : 0;
+  uint8_t* dst = packed + (size_t)chunk * 8192;
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    const int n = e >> 6, k = e & 63;
+    const int rc = enc_ref_col(n);
+    const float v = rc < 0 ? 0.f : W[(size_t)(kb * 64 + k) * ldw + colbase + rc];
+    *reinterpret_cast<uint16_t*>(dst + sw128_offset(n, k)) = split1<false>(v, part);
+  }
+}
+
+struct EncGradParams {
+  const uint8_t* packed;      // 16 chunks of 8 KB
+  Images img;
+  const float* t;             // [M]
+  float* d_origins;           // [R,3] (+=), may be NULL
+  float* d_dirs;              // [R,3] (+=), may be NULL
+  long long M;
+  int S, num_tiles;
+};
+
+__global__ void __launch_bounds__(192, 1) tc_mlp_encgrad_kernel(const EncGradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_w = smem;
+  uint8_t* s_a = smem + kEgWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_a + kEgStages * kEgStageBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kEgStages;
+  uint64_t* w_ready = bars + 2 * kEgStages;
+  uint64_t* d_full = w_ready + 1;
+  uint64_t* d_empty = w_ready + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_ready + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kEgStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    mbar_init(w_ready, 1);
+    mbar_init(d_full, 1);
+    mbar_init(d_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_ready, kEgWBytes);
+      for (int c = 0; c < 16; ++c) bulk_g2s(s_w + c * 8192, p.packed + (size_t)c * 8192, 8192, w_ready);
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        for (int li = 0; li < 2; ++li) {
+          const int tg = li == 0 ? t_g(4) : t_g(0);
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&a_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&a_full[stage], kEgStageBytes);
+            bulk_g2s(s_a + stage * kEgStageBytes, p.img.at(tg, tile, kb, 0), kChunkBytes, &a_full[stage]);
+            bulk_g2s(s_a + stage * kEgStageBytes + kChunkBytes, p.img.at(tg, tile, kb, 1), kChunkBytes, &a_full[stage]);
+            if (++stage == kEgStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, 64, 1);
+      mbar_wait(w_ready, 0);
+      tc_fence_after();
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(d_empty, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int li = 0; li < 2; ++li) {
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(&a_full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(s_a + stage * kEgStageBytes), a_lo = a_hi + kChunkBytes;
+            const uint32_t w_hi = smem_u32(s_w + ((li * 4 + kb) * 2) * 8192), w_lo = w_hi + 8192;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_ss(tmem_base, make_smem_desc(a_hi + ks * 32), make_smem_desc(w_hi + ks * 32), idesc, (li | kb | ks) != 0);
+              umma_ss(tmem_base, make_smem_desc(a_lo + ks * 32), make_smem_desc(w_hi + ks * 32), idesc, 1u);
+              umma_ss(tmem_base, make_smem_desc(a_hi + ks * 32), make_smem_desc(w_lo + ks * 32), idesc, 1u);
+            }
+            umma_commit(&a_empty[stage]);
+            if (++stage == kEgStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(d_full);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const long long m = (long long)tile * kTileM + row;
+      const bool valid = m < p.M;
+      mbar_wait(d_full, it & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v0);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty);
+      // encoder values of this row (hi + lo image), internal column order
+      float gx[3] = {0.f, 0.f, 0.f};
+      {
+        const uint8_t* eh = p.img.at(T_ENC, tile, 0, 0);
+        const uint8_t* el = p.img.at(T_ENC, tile, 0, 1);
+        float g[64];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { g[i] = __uint_as_float(v0[i]); g[32 + i] = __uint_as_float(v1[i]); }
+        gx[0] = g[0]; gx[1] = g[1]; gx[2] = g[2];
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float e[8];
+          const uint32_t off = sw128_offset(row, c8 * 8);
+          unpack8(*reinterpret_cast<const uint4*>(eh + off), *reinterpret_cast<const uint4*>(el + off), e);
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const int ic = c8 * 8 + i;               // (sin, cos) pair at internal columns ic, ic+1 (ic >= 4)
+            if (ic < 4) continue;
+            const int pr = (ic - 4) >> 1, c = pr / kL, j = pr - c * kL;
+            const float f = band_freq(j);
+            const float contrib = f * (g[ic] * e[i + 1] - g[ic + 1] * e[i]);
+            if (c == 0) gx[0] += contrib; else if (c == 1) gx[1] += contrib; else gx[2] += contrib;
+          }
+        }
+      }
+      const float tv = valid ? p.t[m] : 0.f;
+      float so[3], sd[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { so[c] = valid ? gx[c] : 0.f; sd[c] = so[c] * tv; }
+      // rows of one warp usually belong to one ray (S multiple of 32): reduce before the atomics
+      const long long ray = valid ? m / p.S : -1;
+      const long long ray0 = __shfl_sync(0xffffffffu, ray, 0);
+      const bool uniform = __all_sync(0xffffffffu, ray == ray0);
+      if (uniform) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) {
+            so[c] += __shfl_xor_sync(0xffffffffu, so[c], s);
+            sd[c] += __shfl_xor_sync(0xffffffffu, sd[c], s);
+          }
+        }
+        if (lane == 0 && ray0 >= 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (p.d_origins) atomicAdd(p.d_origins + ray0 * 3 + c, so[c]);
+            if (p.d_dirs) atomicAdd(p.d_dirs + ray0 * 3 + c, sd[c]);
+          }
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (p.d_origins) atomicAdd(p.d_origins + ray * 3 + c, so[c]);
+          if (p.d_dirs) atomicAdd(p.d_dirs + ray * 3 + c, sd[c]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+// view-direction part: Gdenc[r][k] = sum_n rayS[r][n] * W8[n][256 + k]
+__global__ void ray_head_dgrad_kernel(int R, const float* __restrict__ rayS, const float* __restrict__ w8,
+                                      float* __restrict__ gdenc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * 32) return;
+  const int r = idx >> 5, k = idx & 31;
+  float acc = 0.f;
+  if (k < kEv)
+    for (int n = 0; n < kHW; ++n) acc = fmaf(rayS[(size_t)r * kHW + n], w8[(size_t)n * (kW + kEv) + kW + k], acc);
+  gdenc[idx] = acc;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -975,7 +1178,8 @@ static size_t images_bytes(int ntiles, size_t* off) {
 
 struct BwdCarve {
   uint8_t *packed_f, *packed_b, *images;
-  float *raybias, *denc, *sigma, *rgb, *g_raw, *g_pre, *rayS;
+  float *raybias, *denc, *sigma, *rgb, *g_raw, *g_pre, *rayS, *gdenc;
+  uint8_t* packed_e;
   WgradJob* jobs;
   ReduceJob* rjobs;
   size_t total;
@@ -992,10 +1196,11 @@ static BwdCarve bwd_carve(void* ws, int nr, int S) {
   size_t o_rb = take((size_t)nr * kHW * 4), o_de = take((size_t)nr * 32 * 4), o_si = take(Mc * 4), o_rg = take(Mc * 12);
   size_t o_gr = take(Mc * 4), o_gp = take(Mc * 16), o_rs = take((size_t)nr * kHW * 4), o_jb = take(256 * sizeof(WgradJob));
   size_t o_rj = take(16 * sizeof(ReduceJob));
+  size_t o_gd = take((size_t)nr * 32 * 4), o_pe = take(kEgWBytes);
   size_t o_im = take(images_bytes(ntiles, nullptr));
   c.packed_f = b + o_pf; c.packed_b = b + o_pb; c.raybias = (float*)(b + o_rb); c.denc = (float*)(b + o_de);
   c.sigma = (float*)(b + o_si); c.rgb = (float*)(b + o_rg); c.g_raw = (float*)(b + o_gr); c.g_pre = (float*)(b + o_gp);
-  c.rayS = (float*)(b + o_rs); c.jobs = (WgradJob*)(b + o_jb); c.rjobs = (ReduceJob*)(b + o_rj); c.images = b + o_im;
+  c.rayS = (float*)(b + o_rs); c.jobs = (WgradJob*)(b + o_jb); c.rjobs = (ReduceJob*)(b + o_rj); c.gdenc = (float*)(b + o_gd); c.packed_e = b + o_pe; c.images = b + o_im;
   c.total = o + 1024;
   return c;
 }
@@ -1003,8 +1208,7 @@ static BwdCarve bwd_carve(void* ws, int nr, int S) {
 size_t tc_workspace_bytes(const SparfMLP* mlp, int R, int S, int backward, int engine) {
   if (backward) {
     int nr = std::min(R, bwd_chunk_rays(S));
-    // ray gradients are served by the SIMT engine for now: size for whichever is larger
-    return std::max(bwd_carve(nullptr, nr, S).total, simt_workspace_bytes(mlp, R, S, 1));
+    return bwd_carve(nullptr, nr, S).total;
   }
   return align_up((size_t)kChunksPerTile * kChunkBytes, 256) + align_up((size_t)R * kHW * sizeof(float), 256) + 256;
 }
@@ -1040,6 +1244,7 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_encgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgSmem + 1024));
     attr_set = true;
   }
   int grid = std::min(p.num_tiles, num_sms());
@@ -1081,11 +1286,6 @@ int tc_mlp_backward(const SparfMLP* mlp, int engine, int R, int S, const float* 
                     size_t workspace_bytes, cudaStream_t st) {
   int rc = simt_validate(mlp);
   if (rc) return rc;
-  if (d_origins != nullptr || d_dirs != nullptr) {
-    // gradients w.r.t. the rays (camera-pose optimisation) are served by the fp32 SIMT engine
-    return simt_mlp_backward(mlp, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace,
-                             workspace_bytes, st);
-  }
   if (!tc_supports(mlp)) {
     set_error("tcgen05 engine: unsupported MLP shape");
     return SPARF_ERR_UNSUPPORTED;
@@ -1176,6 +1376,26 @@ int tc_mlp_backward(const SparfMLP* mlp, int engine, int R, int S, const float* 
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
     ray_head_wgrad_kernel<<<ceil_div(nr, 64), 128, 0, st>>>(nr, 64, c.rayS, c.denc, grad->head_w[0]);
     SPARF_CHECK_LAUNCH("ray_head_wgrad_kernel");
+
+    // 5. gradients w.r.t. the rays (camera-pose optimisation)
+    if (d_origins != nullptr || d_dirs != nullptr) {
+      pack_weights_enc_kernel<<<16, 256, 0, st>>>(mlp->trunk_w[4], mlp->trunk_w[0], c.packed_e);
+      SPARF_CHECK_LAUNCH("pack_weights_enc_kernel");
+      EncGradParams ep;
+      ep.packed = c.packed_e; ep.img = img; ep.t = t + m0;
+      ep.d_origins = d_origins ? d_origins + (size_t)r0 * 3 : nullptr;
+      ep.d_dirs = d_dirs ? d_dirs + (size_t)r0 * 3 : nullptr;
+      ep.M = Mc; ep.S = S; ep.num_tiles = ntiles;
+      tc_mlp_encgrad_kernel<<<std::min(ntiles, num_sms()), 192, kEgSmem + 1024, st>>>(ep);
+      SPARF_CHECK_LAUNCH("tc_mlp_encgrad_kernel");
+      if (d_dirs) {
+        ray_head_dgrad_kernel<<<ceil_div(nr * 32, 256), 256, 0, st>>>(nr, c.rayS, mlp->head_w[0], c.gdenc);
+        SPARF_CHECK_LAUNCH("ray_head_dgrad_kernel");
+        direnc_bwd_kernel<<<ceil_div(nr, 128), 128, 0, st>>>(nr, kLv, 32, c.denc, c.gdenc, dirs + (size_t)r0 * 3,
+                                                             d_dirs + (size_t)r0 * 3);
+        SPARF_CHECK_LAUNCH("direnc_bwd_kernel");
+      }
+    }
   }
   return SPARF_OK;
 }
