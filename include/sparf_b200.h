@@ -141,6 +141,22 @@ int sparf_mlp_backward(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S
                        const float* d_rgb, const SparfMLPGrad* grad, float* d_origins, float* d_dirs,
                        void* workspace, size_t workspace_bytes, sparf_stream_t stream);
 
+/* Tape variants (tcgen05 engine): the TRAINING forward additionally dumps, into a caller-held `tape`, the per-layer
+ * operand images the backward needs, so that sparf_mlp_backward_tape skips the recompute.  The tape must stay
+ * untouched between the two calls.  sparf_mlp_tape_bytes returns 0 when no tape is available for this call
+ * (SIMT engine, unsupported shape, or a batch larger than one backward chunk): use the recompute pair then.
+ * Outputs and numerics of the forward are identical to sparf_mlp_forward. */
+size_t sparf_mlp_tape_bytes(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S);
+int sparf_mlp_forward_tape(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S, const float* origins,
+                           const float* dirs, const float* t, const float* noise, float* sigma, float* rgb,
+                           void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes,
+                           sparf_stream_t stream);
+int sparf_mlp_backward_tape(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S, const float* origins,
+                            const float* dirs, const float* t, const float* sigma, const float* rgb,
+                            const float* d_sigma, const float* d_rgb, const SparfMLPGrad* grad, float* d_origins,
+                            float* d_dirs, void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes,
+                            sparf_stream_t stream);
+
 /* ---------------------------------------------------------------- compositing
  * NeRF.composite (frequency_nerf.py:283-343).  Outputs: rgb_map [R,3], depth/opacity/depth_var/rgb_var
  * [R], weights [R,S], all_cumulated [R] (= T at sample S-2).  white_bg: rgb += 1 - opacity.

@@ -46,6 +46,11 @@ _SIGNATURES = {
     "sparf_mlp_forward": (c_int32, [POINTER(SparfMLP), c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "sparf_mlp_backward": (c_int32, [POINTER(SparfMLP), c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P,
                                      POINTER(SparfMLPGrad), _P, _P, _P, c_size_t, _P]),
+    "sparf_mlp_tape_bytes": (c_size_t, [POINTER(SparfMLP), c_int32, c_int32, c_int32]),
+    "sparf_mlp_forward_tape": (c_int32, [POINTER(SparfMLP), c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P, c_size_t,
+                                         _P, c_size_t, _P]),
+    "sparf_mlp_backward_tape": (c_int32, [POINTER(SparfMLP), c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, _P,
+                                          POINTER(SparfMLPGrad), _P, _P, _P, c_size_t, _P, c_size_t, _P]),
     "sparf_composite_forward": (c_int32, [c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sparf_composite_backward": (c_int32, [c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sparf_huber2_fwd_bwd": (c_int32, [c_int64, _P, _P, c_float, _P, _P, _P]),

@@ -107,3 +107,44 @@ extern "C" int sparf_mlp_backward(const SparfMLP* mlp, int32_t engine, int32_t R
   set_error("mlp_backward: engine %d not available in this build", engine);
   return SPARF_ERR_UNSUPPORTED;
 }
+
+// ---------------------------------------------------------------- tape variants (training forward keeps the
+// operand images so that the backward does not recompute the forward)
+extern "C" size_t sparf_mlp_tape_bytes(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S) {
+  if (!mlp || R <= 0 || S <= 0) return 0;
+  engine = resolve_engine(mlp, engine);
+#ifdef SPARF_WITH_TC
+  if (engine == SPARF_ENGINE_TC_3X) return tc_tape_bytes(mlp, R, S);
+#endif
+  return 0;
+}
+
+extern "C" int sparf_mlp_forward_tape(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S, const float* origins,
+                                      const float* dirs, const float* t, const float* noise, float* sigma, float* rgb,
+                                      void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes,
+                                      sparf_stream_t stream) {
+  SPARF_REQUIRE(mlp && R > 0 && S > 0 && origins && dirs && t && sigma && rgb && tape, "mlp_forward_tape: bad arguments");
+#ifdef SPARF_WITH_TC
+  if (resolve_engine(mlp, engine) == SPARF_ENGINE_TC_3X)
+    return tc_mlp_forward_tape(mlp, SPARF_ENGINE_TC_3X, R, S, origins, dirs, t, noise, sigma, rgb, tape, tape_bytes, workspace,
+                               workspace_bytes, (cudaStream_t)stream);
+#endif
+  set_error("mlp_forward_tape: only the tcgen05 engine keeps a tape (sparf_mlp_tape_bytes returned 0)");
+  return SPARF_ERR_UNSUPPORTED;
+}
+
+extern "C" int sparf_mlp_backward_tape(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S, const float* origins,
+                                       const float* dirs, const float* t, const float* sigma, const float* rgb,
+                                       const float* d_sigma, const float* d_rgb, const SparfMLPGrad* grad,
+                                       float* d_origins, float* d_dirs, void* tape, size_t tape_bytes, void* workspace,
+                                       size_t workspace_bytes, sparf_stream_t stream) {
+  SPARF_REQUIRE(mlp && R > 0 && S > 0 && origins && dirs && t && sigma && rgb && d_sigma && d_rgb && grad && tape,
+                "mlp_backward_tape: bad arguments");
+#ifdef SPARF_WITH_TC
+  if (resolve_engine(mlp, engine) == SPARF_ENGINE_TC_3X)
+    return tc_mlp_backward_tape(mlp, SPARF_ENGINE_TC_3X, R, S, origins, dirs, t, sigma, rgb, d_sigma, d_rgb, grad, d_origins,
+                                d_dirs, tape, tape_bytes, workspace, workspace_bytes, (cudaStream_t)stream);
+#endif
+  set_error("mlp_backward_tape: only the tcgen05 engine keeps a tape");
+  return SPARF_ERR_UNSUPPORTED;
+}

@@ -81,10 +81,9 @@ enum { T_ENC = 0, T_H0 = 1, T_FEAT = 8, T_HID = 9, T_GHID = 10, T_G7F = 11, T_G6
 __host__ __device__ constexpr int tensor_nblk(int t) { return t == T_ENC ? 1 : ((t == T_HID || t == T_GHID) ? 2 : 4); }
 __host__ __device__ constexpr int t_g(int l) { return T_G6 + (6 - l); }   // image of dL/dz_l, l = 0..6
 struct Images {
-  uint8_t* base;
-  size_t off[T_COUNT];
+  uint8_t* ptr[T_COUNT];   // forward tensors (t < T_GHID) may live in a caller-held tape, gradients in the workspace
   __host__ __device__ uint8_t* at(int t, int tile, int blk, int part) const {
-    return base + off[t] + ((((size_t)tile * tensor_nblk(t)) + blk) * 2 + part) * kChunkBytes;
+    return ptr[t] + ((((size_t)tile * tensor_nblk(t)) + blk) * 2 + part) * kChunkBytes;
   }
 };
 
@@ -257,9 +256,20 @@ __device__ __forceinline__ void split_store32(const float (&f)[32], int row, int
       *reinterpret_cast<uint4*>(s_hi + off) = vh;
       *reinterpret_cast<uint4*>(s_lo + off) = vl;
     }
-    if (g_hi) {
+    if (g_hi && !kF16) {
       *reinterpret_cast<uint4*>(g_hi + off) = vh;
       *reinterpret_cast<uint4*>(g_lo + off) = vl;
+    }
+  }
+  if (kF16 && g_hi) {   // the HBM images feed the gradient kernels, which work on bf16 halves
+    uint32_t bh[16], bl[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) split2<false>(f[2 * i], f[2 * i + 1], bh[i], bl[i]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t off = sw128_offset(row, col0 + c * 8);
+      *reinterpret_cast<uint4*>(g_hi + off) = make_uint4(bh[4 * c], bh[4 * c + 1], bh[4 * c + 2], bh[4 * c + 3]);
+      *reinterpret_cast<uint4*>(g_lo + off) = make_uint4(bl[4 * c], bl[4 * c + 1], bl[4 * c + 2], bl[4 * c + 3]);
     }
   }
 }
@@ -1163,21 +1173,27 @@ bool tc_supports(const SparfMLP* mlp) {
 }
 
 bool tc_backward_available() { return true; }
+static int tape_tiles(int R, int S);
 
 // rays per backward chunk: <= 1024 row tiles of saved images (~2.3 GB)
 static int bwd_chunk_rays(int S) { return std::max(1, (1024 * kTileM) / S); }
 
-static size_t images_bytes(int ntiles, size_t* off) {
+static size_t images_bytes(int ntiles, int t_begin, int t_end) {
   size_t total = 0;
-  for (int t = 0; t < T_COUNT; ++t) {
-    if (off) off[t] = total;
-    total += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles;
-  }
+  for (int t = t_begin; t < t_end; ++t) total += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles;
   return total;
+}
+static size_t fwd_images_bytes(int ntiles) { return images_bytes(ntiles, 0, T_GHID); }
+static size_t bwd_images_bytes(int ntiles) { return images_bytes(ntiles, T_GHID, T_COUNT); }
+static void images_assign(Images& img, int ntiles, uint8_t* fwd_base, uint8_t* bwd_base) {
+  size_t o = 0;
+  for (int t = 0; t < T_GHID; ++t) { img.ptr[t] = fwd_base ? fwd_base + o : nullptr; o += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles; }
+  o = 0;
+  for (int t = T_GHID; t < T_COUNT; ++t) { img.ptr[t] = bwd_base ? bwd_base + o : nullptr; o += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles; }
 }
 
 struct BwdCarve {
-  uint8_t *packed_f, *packed_b, *images;
+  uint8_t *packed_f, *packed_b, *images_f, *images_b;
   float *raybias, *denc, *sigma, *rgb, *g_raw, *g_pre, *rayS, *gdenc;
   uint8_t* packed_e;
   WgradJob* jobs;
@@ -1185,7 +1201,7 @@ struct BwdCarve {
   size_t total;
 };
 
-static BwdCarve bwd_carve(void* ws, int nr, int S) {
+static BwdCarve bwd_carve(void* ws, int nr, int S, bool with_fwd_images) {
   const size_t Mc = (size_t)nr * S;
   const int ntiles = (int)((Mc + kTileM - 1) / kTileM);
   size_t o = 0;
@@ -1197,10 +1213,11 @@ static BwdCarve bwd_carve(void* ws, int nr, int S) {
   size_t o_gr = take(Mc * 4), o_gp = take(Mc * 16), o_rs = take((size_t)nr * kHW * 4), o_jb = take(256 * sizeof(WgradJob));
   size_t o_rj = take(16 * sizeof(ReduceJob));
   size_t o_gd = take((size_t)nr * 32 * 4), o_pe = take(kEgWBytes);
-  size_t o_im = take(images_bytes(ntiles, nullptr));
+  size_t o_ib = take(bwd_images_bytes(ntiles));
+  size_t o_if = take(with_fwd_images ? fwd_images_bytes(ntiles) : 0);
   c.packed_f = b + o_pf; c.packed_b = b + o_pb; c.raybias = (float*)(b + o_rb); c.denc = (float*)(b + o_de);
   c.sigma = (float*)(b + o_si); c.rgb = (float*)(b + o_rg); c.g_raw = (float*)(b + o_gr); c.g_pre = (float*)(b + o_gp);
-  c.rayS = (float*)(b + o_rs); c.jobs = (WgradJob*)(b + o_jb); c.rjobs = (ReduceJob*)(b + o_rj); c.gdenc = (float*)(b + o_gd); c.packed_e = b + o_pe; c.images = b + o_im;
+  c.rayS = (float*)(b + o_rs); c.jobs = (WgradJob*)(b + o_jb); c.rjobs = (ReduceJob*)(b + o_rj); c.gdenc = (float*)(b + o_gd); c.packed_e = b + o_pe; c.images_b = b + o_ib; c.images_f = with_fwd_images ? b + o_if : nullptr;
   c.total = o + 1024;
   return c;
 }
@@ -1208,7 +1225,7 @@ static BwdCarve bwd_carve(void* ws, int nr, int S) {
 size_t tc_workspace_bytes(const SparfMLP* mlp, int R, int S, int backward, int engine) {
   if (backward) {
     int nr = std::min(R, bwd_chunk_rays(S));
-    return bwd_carve(nullptr, nr, S).total;
+    return bwd_carve(nullptr, nr, S, true).total;
   }
   return align_up((size_t)kChunksPerTile * kChunkBytes, 256) + align_up((size_t)R * kHW * sizeof(float), 256) + 256;
 }
@@ -1237,7 +1254,7 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
   p.num_tiles = (int)((p.M + kTileM - 1) / kTileM);
   p.passes = passes;
   p.save = img != nullptr;
-  if (img) p.img = *img; else { p.img.base = nullptr; }
+  if (img) p.img = *img; else { for (int i = 0; i < T_COUNT; ++i) p.img.ptr[i] = nullptr; }
   static bool attr_set = false;
   if (!attr_set) {
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
@@ -1280,10 +1297,77 @@ int tc_mlp_forward(const SparfMLP* mlp, int engine, int R, int S, const float* o
                         raybias, nullptr, st);
 }
 
+// Training forward: same fp16-split arithmetic and outputs as tc_mlp_forward, plus the tape for the backward.
+int tc_mlp_forward_tape(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
+                        const float* t, const float* noise, float* sigma, float* rgb, void* tape, size_t tape_bytes,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  int rc = simt_validate(mlp);
+  if (rc) return rc;
+  const size_t need = tc_tape_bytes(mlp, R, S);
+  if (need == 0 || tape == nullptr || tape_bytes < need) {
+    set_error("tc_mlp_forward_tape: tape unsupported for this call or too small (%zu < %zu bytes)", tape_bytes, need);
+    return SPARF_ERR_WORKSPACE;
+  }
+  if (workspace_bytes < tc_workspace_bytes(mlp, R, S, 0, engine)) {
+    set_error("tc_mlp_forward_tape: workspace %zu < %zu bytes", workspace_bytes, tc_workspace_bytes(mlp, R, S, 0, engine));
+    return SPARF_ERR_WORKSPACE;
+  }
+  uint8_t* packed = reinterpret_cast<uint8_t*>(workspace);
+  float* raybias = reinterpret_cast<float*>(packed + align_up((size_t)kChunksPerTile * kChunkBytes, 256));
+  const int ntiles = tape_tiles(R, S);
+  uint8_t* tp = reinterpret_cast<uint8_t*>(tape);
+  float* denc = reinterpret_cast<float*>(tp + align_up(fwd_images_bytes(ntiles), 1024));
+  PackParams pp;
+  fill_pack_params(mlp, pp, packed);
+  pack_weights_kernel<true><<<kChunksPerTile, 256, 0, st>>>(pp);
+  SPARF_CHECK_LAUNCH("pack_weights_kernel");
+  C2F c2f{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
+  raybias_kernel<<<ceil_div(R, 4), 512, 0, st>>>(R, dirs, mlp->head_w[0], mlp->head_b[0], c2f, raybias, denc);
+  SPARF_CHECK_LAUNCH("raybias_kernel");
+  Images img;
+  images_assign(img, ntiles, tp, nullptr);
+  return launch_forward(mlp, true, 3, R, S, origins, dirs, t, noise, sigma, rgb, packed, raybias, &img, st);
+}
+
+// tape = what the training forward keeps for the backward: the forward operand images of every row tile
+// followed by the per-ray view-direction encoding [R,32]
+static int tape_tiles(int R, int S) { return (int)(((long long)R * S + kTileM - 1) / kTileM); }
+size_t tc_tape_bytes(const SparfMLP* mlp, int R, int S) {
+  if (!tc_supports(mlp) || R > bwd_chunk_rays(S)) return 0;   // larger batches recompute chunk by chunk
+  return align_up(fwd_images_bytes(tape_tiles(R, S)), 1024) + align_up((size_t)R * 32 * 4, 1024);
+}
+
+static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
+                                const float* t, const float* noise, const float* d_sigma, const float* d_rgb,
+                                const SparfMLPGrad* grad, float* d_origins, float* d_dirs, void* workspace,
+                                size_t workspace_bytes, uint8_t* tape, const float* sigma_fwd, const float* rgb_fwd,
+                                cudaStream_t st);
+
 int tc_mlp_backward(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
                     const float* t, const float* noise, const float* d_sigma, const float* d_rgb,
                     const SparfMLPGrad* grad, float* d_origins, float* d_dirs, void* workspace,
                     size_t workspace_bytes, cudaStream_t st) {
+  return tc_mlp_backward_impl(mlp, engine, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace,
+                              workspace_bytes, nullptr, nullptr, nullptr, st);
+}
+
+int tc_mlp_backward_tape(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
+                         const float* t, const float* sigma, const float* rgb, const float* d_sigma, const float* d_rgb,
+                         const SparfMLPGrad* grad, float* d_origins, float* d_dirs, void* tape, size_t tape_bytes,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (tape == nullptr || tape_bytes < tc_tape_bytes(mlp, R, S) || tc_tape_bytes(mlp, R, S) == 0) {
+    set_error("tc_mlp_backward_tape: tape missing or too small (%zu < %zu bytes)", tape_bytes, tc_tape_bytes(mlp, R, S));
+    return SPARF_ERR_WORKSPACE;
+  }
+  return tc_mlp_backward_impl(mlp, engine, R, S, origins, dirs, t, nullptr, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace,
+                              workspace_bytes, reinterpret_cast<uint8_t*>(tape), sigma, rgb, st);
+}
+
+static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
+                                const float* t, const float* noise, const float* d_sigma, const float* d_rgb,
+                                const SparfMLPGrad* grad, float* d_origins, float* d_dirs, void* workspace,
+                                size_t workspace_bytes, uint8_t* tape, const float* sigma_fwd, const float* rgb_fwd,
+                                cudaStream_t st) {
   int rc = simt_validate(mlp);
   if (rc) return rc;
   if (!tc_supports(mlp)) {
@@ -1301,25 +1385,32 @@ int tc_mlp_backward(const SparfMLP* mlp, int engine, int R, int S, const float* 
     const long long Mc = (long long)nr * S;
     const size_t m0 = (size_t)r0 * S;
     const int ntiles = (int)((Mc + kTileM - 1) / kTileM);
-    BwdCarve c = bwd_carve(workspace, nr, S);
+    BwdCarve c = bwd_carve(workspace, nr, S, tape == nullptr);
     Images img;
-    img.base = c.images;
-    images_bytes(ntiles, img.off);
+    images_assign(img, ntiles, tape ? tape : c.images_f, c.images_b);
+    if (tape) {   // single chunk by construction (tc_tape_bytes): forward images + denc come from the tape
+      c.denc = reinterpret_cast<float*>(tape + align_up(fwd_images_bytes(ntiles), 1024));
+      c.sigma = const_cast<float*>(sigma_fwd);
+      c.rgb = const_cast<float*>(rgb_fwd);
+    }
 
     PackParams pp;
-    fill_pack_params(mlp, pp, c.packed_f);
-    pack_weights_kernel<false><<<kChunksPerTile, 256, 0, st>>>(pp);
-    SPARF_CHECK_LAUNCH("pack_weights_kernel<bf16>");
+    if (!tape) {
+      fill_pack_params(mlp, pp, c.packed_f);
+      pack_weights_kernel<false><<<kChunksPerTile, 256, 0, st>>>(pp);
+      SPARF_CHECK_LAUNCH("pack_weights_kernel<bf16>");
+    }
     fill_pack_params(mlp, pp, c.packed_b);
     pack_weights_bwd_kernel<<<kBwdChunksPerTile, 256, 0, st>>>(pp);
     SPARF_CHECK_LAUNCH("pack_weights_bwd_kernel");
-    raybias_kernel<<<ceil_div(nr, 4), 512, 0, st>>>(nr, dirs + (size_t)r0 * 3, mlp->head_w[0], mlp->head_b[0], c2f, c.raybias, c.denc);
-    SPARF_CHECK_LAUNCH("raybias_kernel");
-
-    // 1. forward re-run (bf16 halves) dumping the operand images
-    rc = launch_forward(mlp, false, 3, nr, S, origins + (size_t)r0 * 3, dirs + (size_t)r0 * 3, t + m0,
-                        noise ? noise + m0 : nullptr, c.sigma, c.rgb, c.packed_f, c.raybias, &img, st);
-    if (rc) return rc;
+    if (!tape) {
+      raybias_kernel<<<ceil_div(nr, 4), 512, 0, st>>>(nr, dirs + (size_t)r0 * 3, mlp->head_w[0], mlp->head_b[0], c2f, c.raybias, c.denc);
+      SPARF_CHECK_LAUNCH("raybias_kernel");
+      // 1. forward re-run (bf16 halves) dumping the operand images
+      rc = launch_forward(mlp, false, 3, nr, S, origins + (size_t)r0 * 3, dirs + (size_t)r0 * 3, t + m0,
+                          noise ? noise + m0 : nullptr, c.sigma, c.rgb, c.packed_f, c.raybias, &img, st);
+      if (rc) return rc;
+    }
 
     // 2. input-gradient chain
     BwdParams bp;

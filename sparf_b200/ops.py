@@ -15,6 +15,8 @@ from . import _lib
 from ._lib import SparfMLP, SparfMLPGrad, check
 
 _ENGINE = [_lib.ENGINE_AUTO]
+# keep the training forward's operand images for the backward (tcgen05 engine); False = always recompute
+USE_TAPE = [True]
 
 # optional device-side timing of the MLP kernels (bench.py roofline): CUDA events on the launching stream
 PROFILE_ON = [False]
@@ -145,19 +147,36 @@ class MLPFunction(torch.autograd.Function):
         rgb = torch.empty(R, S, 3, device=t.device, dtype=torch.float32)
         nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 0, engine)
         ws = _workspace(nbytes, t.device)
+        # Training forward: when a gradient will be asked for and the engine offers it, keep a "tape" (the
+        # per-layer operand images) so that the backward skips the forward recompute.
+        wants_grad = any(ctx.needs_input_grad[i] for i in (2, 3)) or any(ctx.needs_input_grad[7:])
+        tape_bytes = L.sparf_mlp_tape_bytes(ctypes.byref(m), engine, R, S) if (wants_grad and USE_TAPE[0]) else 0
+        ctx.tape = None
         with _timed("mlp_forward"):
-            check(L.sparf_mlp_forward(ctypes.byref(m), engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t), _ptr(noise_c),
-                                      _ptr(sigma), _ptr(rgb), _ptr(ws), ws.numel(), _stream()), "mlp_forward")
+            if tape_bytes:
+                ctx.tape = torch.empty(tape_bytes, dtype=torch.uint8, device=t.device)
+                check(L.sparf_mlp_forward_tape(ctypes.byref(m), engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t),
+                                               _ptr(noise_c), _ptr(sigma), _ptr(rgb), _ptr(ctx.tape), tape_bytes, _ptr(ws),
+                                               ws.numel(), _stream()), "mlp_forward_tape")
+            else:
+                check(L.sparf_mlp_forward(ctypes.byref(m), engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t), _ptr(noise_c),
+                                          _ptr(sigma), _ptr(rgb), _ptr(ws), ws.numel(), _stream()), "mlp_forward")
         ctx.spec, ctx.engine = spec, engine
         ctx.noise = noise_c
         ctx.progress = progress
-        ctx.save_for_backward(origins, dirs, t, *params)
+        if ctx.tape is not None:
+            ctx.save_for_backward(origins, dirs, t, sigma, rgb, *params)
+        else:
+            ctx.save_for_backward(origins, dirs, t, *params)
         return sigma, rgb
 
     @staticmethod
     def backward(ctx, g_sigma, g_rgb):
         L = _lib.lib()
-        origins, dirs, t, *params = ctx.saved_tensors
+        if ctx.tape is not None:
+            origins, dirs, t, sigma_f, rgb_f, *params = ctx.saved_tensors
+        else:
+            origins, dirs, t, *params = ctx.saved_tensors
         spec = ctx.spec
         R, S = t.shape
         g_sigma = _f32c(g_sigma) if g_sigma is not None else torch.zeros(R, S, device=t.device)
@@ -176,9 +195,16 @@ class MLPFunction(torch.autograd.Function):
         nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 1, ctx.engine)
         ws = _workspace(nbytes, t.device)
         with _timed("mlp_backward"):
-            check(L.sparf_mlp_backward(ctypes.byref(m), ctx.engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t),
-                                       _ptr(ctx.noise), _ptr(g_sigma), _ptr(g_rgb), ctypes.byref(gs), _ptr(d_o), _ptr(d_d),
-                                       _ptr(ws), ws.numel(), _stream()), "mlp_backward")
+            if ctx.tape is not None:
+                check(L.sparf_mlp_backward_tape(ctypes.byref(m), ctx.engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t),
+                                                _ptr(sigma_f), _ptr(rgb_f), _ptr(g_sigma), _ptr(g_rgb), ctypes.byref(gs),
+                                                _ptr(d_o), _ptr(d_d), _ptr(ctx.tape), ctx.tape.numel(), _ptr(ws), ws.numel(),
+                                                _stream()), "mlp_backward_tape")
+                ctx.tape = None
+            else:
+                check(L.sparf_mlp_backward(ctypes.byref(m), ctx.engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t),
+                                           _ptr(ctx.noise), _ptr(g_sigma), _ptr(g_rgb), ctypes.byref(gs), _ptr(d_o),
+                                           _ptr(d_d), _ptr(ws), ws.numel(), _stream()), "mlp_backward")
         return (None, None, d_o if need_o else None, d_d if need_d else None, None, None, None, *grads)
 
 

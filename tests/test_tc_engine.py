@@ -117,12 +117,17 @@ def test_tc_backward_matches_simt(R, S, c2f):
     gs = torch.randn(R, S, device="cuda", generator=g) * 1e-3
     gc = torch.randn(R, S, 3, device="cuda", generator=g) * 1e-3
     grads = {}
-    for eng in (_lib.ENGINE_SIMT_FP32, _lib.ENGINE_TC_3X):
+    for eng, tape in ((_lib.ENGINE_SIMT_FP32, True), (_lib.ENGINE_TC_3X, True), (_lib.ENGINE_TC_3X, False)):
+        ops.USE_TAPE[0] = tape     # tcgen05: taped training forward (no recompute) and the recompute path
         ps = [p.clone().requires_grad_(True) for p in params]
         s, c = ops.mlp_forward(spec, o, d, t, ps, noise=noise, progress=prog, engine=eng)
         ((s * gs).sum() + (c * gc).sum()).backward()
         torch.cuda.synchronize()
-        grads[eng] = [p.grad.clone() for p in ps]
+        if eng == _lib.ENGINE_TC_3X and not tape:
+            grads["tc_recompute"] = [p.grad.clone() for p in ps]
+        else:
+            grads[eng] = [p.grad.clone() for p in ps]
+    ops.USE_TAPE[0] = True
     # ground truth: the oracle's formulas in fp64 on the device (autograd)
     from oracle import sparf_oracle as O
     keys = sum([["mlp_feat.%d.weight" % i, "mlp_feat.%d.bias" % i] for i in range(8)], []) + \
@@ -142,6 +147,8 @@ def test_tc_backward_matches_simt(R, S, c2f):
         # within 2e-3 of the exact gradient, or as good as the fp32 engine up to a small factor (both engines
         # see ReLU sign flips of near-zero pre-activations on these ill-conditioned random nets)
         assert e_tc < max(2e-3, 4 * e_simt), (keys[i], e_tc, e_simt)
+        e_rc = ((grads["tc_recompute"][i].double() - tr).abs().max() / den).item()
+        assert e_rc < max(2e-3, 4 * e_simt), (keys[i], "recompute path", e_rc, e_simt)
     print("R=%d S=%d: worst grad rel err vs fp64: tcgen05 %.2e, simt fp32 %.2e" % (R, S, worst_tc, worst_simt))
 
 
