@@ -110,14 +110,10 @@ def make_workload(device, seed=0):
 
 
 def flat_grads(net):
-    """Point every parameter's .grad at a view of ONE flat fp32 buffer (single all-reduce, single zero_)."""
-    params = [p for p in net.parameters() if p.requires_grad]
-    flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device)
-    o = 0
-    for p in params:
-        p.grad = flat[o:o + p.numel()].view_as(p)
-        o += p.numel()
-    return flat
+    """Point every parameter's .grad at a view of ONE flat fp32 buffer (single all-reduce, single zero_); the MLP
+    backward kernels then accumulate straight into it (sparf_b200.distributed.FlatGradients)."""
+    from sparf_b200.distributed import FlatGradients
+    return FlatGradients([net]).flat
 
 
 def run_ours(args):

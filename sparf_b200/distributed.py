@@ -49,6 +49,10 @@ class FlatGradients:
         for p in self.params:
             p.grad = self.flat[o:o + p.numel()].view_as(p)
             o += p.numel()
+        # every parameter now has persistent, contiguous fp32 .grad storage: let the MLP backward kernels
+        # accumulate into it directly (see ops.ACCUMULATE_INTO_PARAM_GRAD)
+        from . import ops
+        ops.ACCUMULATE_INTO_PARAM_GRAD[0] = True
 
     def zero_(self):
         self.flat.zero_()

@@ -17,6 +17,11 @@ from ._lib import SparfMLP, SparfMLPGrad, check
 _ENGINE = [_lib.ENGINE_AUTO]
 # keep the training forward's operand images for the backward (tcgen05 engine); False = always recompute
 USE_TAPE = [True]
+# Opt-in: let the MLP backward accumulate straight into existing `param.grad` storage (the C ABI accumulates, +=)
+# instead of returning fresh gradient tensors for autograd to add.  Saves ~20 tiny kernels and a 2 MB memset per
+# render pass.  Only valid for plain `loss.backward()` training loops (no torch.autograd.grad / grad hooks / DDP
+# hooks on these parameters); sparf_b200.distributed.FlatGradients enables it.
+ACCUMULATE_INTO_PARAM_GRAD = [False]
 
 # optional device-side timing of the MLP kernels (bench.py roofline): CUDA events on the launching stream
 PROFILE_ON = [False]
@@ -164,6 +169,7 @@ class MLPFunction(torch.autograd.Function):
         ctx.spec, ctx.engine = spec, engine
         ctx.noise = noise_c
         ctx.progress = progress
+        ctx.param_refs = params if ACCUMULATE_INTO_PARAM_GRAD[0] else None
         if ctx.tape is not None:
             ctx.save_for_backward(origins, dirs, t, sigma, rgb, *params)
         else:
@@ -182,12 +188,17 @@ class MLPFunction(torch.autograd.Function):
         g_sigma = _f32c(g_sigma) if g_sigma is not None else torch.zeros(R, S, device=t.device)
         g_rgb = _f32c(g_rgb) if g_rgb is not None else torch.zeros(R, S, 3, device=t.device)
         m, keep = spec.fill(params, ctx.progress)
-        sizes = [p.numel() for p in params]
-        flat = torch.zeros(sum(sizes), device=t.device, dtype=torch.float32)
-        grads, o = [], 0
-        for p, n in zip(params, sizes):
-            grads.append(flat[o:o + n].view(p.shape))
-            o += n
+        inplace = ctx.param_refs is not None and all(
+            p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in ctx.param_refs)
+        if inplace:
+            grads = [p.grad for p in ctx.param_refs]
+        else:
+            sizes = [p.numel() for p in params]
+            flat = torch.zeros(sum(sizes), device=t.device, dtype=torch.float32)
+            grads, o = [], 0
+            for p, n in zip(params, sizes):
+                grads.append(flat[o:o + n].view(p.shape))
+                o += n
         gs = spec.grad_struct(grads)
         need_o, need_d = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
         d_o = torch.zeros_like(origins) if (need_o or need_d) else None
@@ -205,6 +216,8 @@ class MLPFunction(torch.autograd.Function):
                 check(L.sparf_mlp_backward(ctypes.byref(m), ctx.engine, R, S, _ptr(origins), _ptr(dirs), _ptr(t),
                                            _ptr(ctx.noise), _ptr(g_sigma), _ptr(g_rgb), ctypes.byref(gs), _ptr(d_o),
                                            _ptr(d_d), _ptr(ws), ws.numel(), _stream()), "mlp_backward")
+        if inplace:
+            grads = [None] * len(grads)
         return (None, None, d_o if need_o else None, d_d if need_d else None, None, None, None, *grads)
 
 
@@ -299,10 +312,28 @@ class RayGenFunction(torch.autograd.Function):
         return d_pose, None, None, None, None
 
 
+_HOST_CACHE = {}
+
+
+def cached(tag: str, tensor: torch.Tensor, fn):
+    """Memoise a small derived quantity of a (device) tensor that rarely changes (intrinsics, depth range), keyed
+    by storage address + in-place version, so that the hot loop neither recomputes it nor synchronises."""
+    key = (tag, tensor.data_ptr(), tensor._version, tuple(tensor.shape), tensor.device)
+    hit = _HOST_CACHE.get(key)
+    if hit is None:
+        if len(_HOST_CACHE) > 256:
+            _HOST_CACHE.clear()
+        # the entry keeps `tensor` alive, so its address cannot be handed to another tensor while cached
+        hit = (fn(tensor), tensor)
+        _HOST_CACHE[key] = hit
+    return hit[0]
+
+
 def raygen(pose_w2c, intr, W: int, *, ray_idx=None, pixels=None):
     """pose_w2c [B,3,4], intr [B,3,3] -> (center, ray) [B,n,3] at ray_idx ((n,)/(B,n) int) or float pixels."""
     assert (ray_idx is None) != (pixels is None)
-    intr_inv = torch.linalg.inv(intr.detach().float())  # camera.py:318-319; intrinsics carry no gradient
+    # camera.py:318-319; intrinsics carry no gradient and are constant over training: invert once
+    intr_inv = cached("Kinv", intr, lambda k: torch.linalg.inv(k.detach().float()))
     return RayGenFunction.apply(pose_w2c, intr_inv, W, ray_idx, pixels)
 
 

@@ -80,6 +80,22 @@ class Graph(torch.nn.Module):
         return opt.nerf.depth.range if opt.nerf.depth.param == "inverse" else data_dict.depth_range[0]
 
     @staticmethod
+    def _range_floats(depth_range):
+        """(near, far, far - near) as python floats carrying the reference's fp32 arithmetic: for metric depth the
+        range is a device tensor (data_dict.depth_range[0]) and `far - near` an fp32 subtraction; for inverse depth
+        a python list.  Device tensors are read back ONCE (cached): no per-step synchronisation."""
+        lo, hi = depth_range[0], depth_range[1]
+        if torch.is_tensor(lo):
+            def read(t):
+                v = t.detach().float().cpu()
+                return float(v[0]), float(v[1]), float(v[1] - v[0])
+            base = depth_range if torch.is_tensor(depth_range) else torch.stack([lo, hi])
+            return ops.cached("range", base, read)
+        near = float(torch.tensor(float(lo), dtype=torch.float32))
+        far = float(torch.tensor(float(hi), dtype=torch.float32))
+        return near, far, float(torch.tensor(float(hi - lo), dtype=torch.float32))
+
+    @staticmethod
     def _fine_disabled(opt, iter, also_absolute=False):
         """True while the schedule keeps the fine network off (renderer.py:317-320, 576-581)."""
         if hasattr(opt.nerf, "ratio_start_fine_sampling_at_x") and opt.nerf.ratio_start_fine_sampling_at_x is not None \
@@ -223,11 +239,8 @@ class Graph(torch.nn.Module):
         rand = None
         if opt.nerf.sample_stratified and mode not in ["val", "eval", "test"]:
             rand = torch.rand(batch_size, num_rays, n_samples, 1, device=self.device).to(self.device)
-        # fp32 arithmetic on the range, as the reference does on its 0-dim tensors / python numbers
-        near = torch.as_tensor(depth_min, dtype=torch.float32)
-        rng = torch.as_tensor(depth_max, dtype=torch.float32) - near if torch.is_tensor(depth_max) \
-            else torch.tensor(float(depth_max - depth_min), dtype=torch.float32)
-        t = ops.sample_depth(batch_size * num_rays, n_samples, float(near), float(rng),
+        near, _, rng = self._range_floats(depth_range)
+        t = ops.sample_depth(batch_size * num_rays, n_samples, near, rng,
                              inverse=(opt.nerf.depth.param == "inverse"), rand=rand, device=self.device)
         return t.view(batch_size, num_rays, n_samples, 1)
 
@@ -241,19 +254,18 @@ class Graph(torch.nn.Module):
 
     def _resample_and_merge(self, opt, weights, t_coarse, depth_range, det):
         B, N, S = weights.shape
-        depth_min, depth_max = depth_range
+        near, far, _ = self._range_floats(depth_range)
         u = self._shared_grid_midpoints(opt.nerf.sample_intvs_fine, det)
-        _, t_all = ops.sample_pdf_merge(weights.reshape(B * N, S), t_coarse.reshape(B * N, S), u,
-                                        float(depth_min), float(depth_max))
+        _, t_all = ops.sample_pdf_merge(weights.reshape(B * N, S), t_coarse.reshape(B * N, S), u, near, far)
         return t_all.view(B, N, -1, 1)
 
     def sample_depth_from_pdf(self, opt, weights, n_samples_coarse, n_samples_fine, depth_range, det):
         """Inverse-transform sampling of the coarse weights [B,N,S] -> [B,N,S_fine,1] (renderer.py:421-456)."""
         B, N, S = weights.shape
-        depth_min, depth_max = depth_range
+        near, far, _ = self._range_floats(depth_range)
         u = self._shared_grid_midpoints(n_samples_fine, det)
         dummy = torch.zeros(B * N, S, device=self.device)
-        t_fine, _ = ops.sample_pdf_merge(weights.reshape(B * N, S), dummy, u, float(depth_min), float(depth_max))
+        t_fine, _ = ops.sample_pdf_merge(weights.reshape(B * N, S), dummy, u, near, far)
         return t_fine.view(B, N, n_samples_fine, 1)
 
     # ---------------------------------------------------------------------------- per-ray far bound
@@ -266,7 +278,7 @@ class Graph(torch.nn.Module):
             intr = intr.unsqueeze(0)
         depth_range = self._depth_range(opt, data_dict)
         ret = self.render_to_max(opt, pose, intr=intr, pixels=pixels, ray_idx=ray_idx, mode=mode, H=H, W=W,
-                                 depth_min=depth_range[0], depth_max=depth_max, iter=iter)
+                                 depth_min=self._range_floats(depth_range)[0], depth_max=depth_max, iter=iter)
         ret.ray_idx = ray_idx
         return ret
 
