@@ -723,6 +723,7 @@ struct WgradJob {
   float* dW;             // destination [*, ldw]
   int ldw, col0;         // row stride and first column
   int enc_cols;          // 1: N' side is the encoder block (internal column order -> reference columns)
+  float* colsum;         // optional: colsum[f] += sum_rows G[row][f]  (the layer's bias gradient), else NULL
 };
 constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 16 * 4096;   // (4 G blocks + 4 X blocks) x (hi, lo) x 32 rows x 128 B
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const WgradJob* __
   const uint32_t tmem_cols = (mhalves * ncols <= 64) ? 64 : (mhalves * ncols <= 128 ? 128 : (mhalves * ncols <= 256 ? 256 : 512));
 
   if (tid == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 5); }   // MMA commit + 4 reducer warps
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -802,9 +803,45 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const WgradJob* __
       umma_commit(done);
     }
   } else {
-    // flush warps 2..5: accumulator rows (= output features) -> atomics on dW
+    // warps 2..5: while the MMA warp streams, reduce the gradient images over the rows straight from the shared
+    // memory stages (bias gradient = column sums of G); at the end flush the accumulator with atomics on dW
     const int q = warp & 3;
     const int rowl = q * 32 + lane;
+    {
+      const int rt = tid - 64;                 // 0..127
+      const int nfeat = job.mblk * 64;
+      float cs0 = 0.f, cs1 = 0.f;
+      uint32_t stage = 0, phase = 0;
+      for (int qi = 0; qi < nq; ++qi) {
+        mbar_wait(&full[stage], phase);
+        if (job.colsum) {
+          const uint8_t* st = smem + stage * kWgStageBytes;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int f = rt + u * 128;
+            if (f < nfeat) {
+              const uint8_t* bh = st + (f >> 6) * 4096;
+              const uint8_t* bl = st + (4 + (f >> 6)) * 4096;
+              float a = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t off = sw128_offset(r, f & 63);
+                a += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(bh + off)) << 16) +
+                     __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(bl + off)) << 16);
+              }
+              if (u == 0) cs0 += a; else cs1 += a;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      if (job.colsum) {
+        if (rt < nfeat) atomicAdd(job.colsum + rt, cs0);
+        if (rt + 128 < nfeat) atomicAdd(job.colsum + rt + 128, cs1);
+      }
+    }
     mbar_wait(done, 0);
     tc_fence_after();
     for (int mh = 0; mh < mhalves; ++mh) {
@@ -1426,23 +1463,25 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     // 3. weight gradients: job table = (layer, slab of row tiles), ~one CTA per SM
     WgradJob jobs[256];
     int nj = 0;
-    auto add_jobs = [&](int tg, int tx, int mblk, int nblk, float* dW, int ldw, int col0, int enc, int slabs) {
+    auto add_jobs = [&](int tg, int tx, int mblk, int nblk, float* dW, int ldw, int col0, int enc, int slabs, float* colsum) {
       slabs = std::max(1, std::min(slabs, ntiles));
       for (int s = 0; s < slabs; ++s) {
         WgradJob j;
         j.t_g = tg; j.t_x = tx; j.mblk = mblk; j.nblk = nblk;
         j.tile_begin = (int)((long long)ntiles * s / slabs);
         j.tile_end = (int)((long long)ntiles * (s + 1) / slabs);
-        j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc;
+        j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum;
         jobs[nj++] = j;
       }
     };
-    add_jobs(T_GHID, T_FEAT, 2, 4, grad->head_w[0], kW + kEv, 0, 0, 9);                       // head 0, feature part
-    add_jobs(T_G7F, T_H0 + 6, 4, 4, grad->trunk_w[7] + kW, kW, 0, 0, 17);                      // trunk 7 rows 1..256
+    // slabs sized so that every CTA streams about the same number of bytes (the kernel is HBM-bound):
+    // per row tile 256 KB (256x256 jobs), 192 KB (head), 160 KB (encoder columns) => 16 / 12 / 10 slabs, 144 CTAs
+    add_jobs(T_GHID, T_FEAT, 2, 4, grad->head_w[0], kW + kEv, 0, 0, 12, grad->head_b[0]);     // head 0, feature part
+    add_jobs(T_G7F, T_H0 + 6, 4, 4, grad->trunk_w[7] + kW, kW, 0, 0, 16, grad->trunk_b[7] + 1);  // trunk 7 rows 1..256
     for (int l = 6; l >= 1; --l)
-      add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 17);
-    add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 5);                        // skip part of layer 4
-    add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 5);                              // layer 0
+      add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 16, grad->trunk_b[l]);
+    add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 10, nullptr);             // skip part of layer 4
+    add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 10, grad->trunk_b[0]);          // layer 0 (+ its bias)
     SPARF_CHECK_CUDA(cudaMemcpyAsync(c.jobs, jobs, sizeof(WgradJob) * nj, cudaMemcpyHostToDevice, st));
     tc_mlp_wgrad_kernel<<<nj, 192, kWgSmem + 1024, st>>>(c.jobs, img);
     SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
@@ -1454,9 +1493,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       ReduceJob j; j.t = t; j.nblk = nblk; j.nc = nc; j.g = g; j.gs = gs; j.out = out; j.ldo = ldo; j.out_bias = ob;
       rj[nrj++] = j;
     };
-    add_red(T_GHID, 2, 0, nullptr, 0, grad->head_b[0], 0, nullptr);
-    add_red(T_G7F, 4, 0, nullptr, 0, grad->trunk_b[7] + 1, 0, nullptr);
-    for (int l = 6; l >= 0; --l) add_red(t_g(l), 4, 0, nullptr, 0, grad->trunk_b[l], 0, nullptr);
+    // (bias gradients = column sums of the gradient images are produced inside the weight-gradient kernel)
     add_red(T_H0 + 6, 4, 1, c.g_raw, 1, grad->trunk_w[7], kW, grad->trunk_b[7]);        // density row of trunk 7
     add_red(T_HID, 2, 3, c.g_pre, 4, grad->head_w[1], kHW, grad->head_b[1]);             // 128 -> 3 colour layer
     SPARF_CHECK_CUDA(cudaMemcpyAsync(c.rjobs, rj, sizeof(ReduceJob) * nrj, cudaMemcpyHostToDevice, st));
