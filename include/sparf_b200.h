@@ -186,6 +186,10 @@ int sparf_tc_selftest(const float* A, const float* B, int32_t K, void* packed, f
 /* Same for the weight-gradient shape: D[128,128] = G[rows,128]^T X[rows,128] through MN-major descriptors. */
 int sparf_tc_selftest_tn(const float* G, const float* X, int32_t rows, float* D, sparf_stream_t stream);
 
+/* Micro-benchmark of cp.async.bulk L2->shared throughput per SM vs copies in flight (tools/probe_bulkcopy.py). */
+int sparf_tc_bulkcopy_probe(const void* src, uint32_t src_bytes, int32_t stages, uint32_t chunk, int32_t iters,
+                            int32_t grid, long long* cycles, sparf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

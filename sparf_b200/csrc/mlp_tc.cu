@@ -28,6 +28,7 @@
 //
 // Reference: NeRF.forward_samples / forward / compute_raw_density (source/models/frequency_nerf.py:149-281).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "mlp_simt.cuh"
@@ -72,7 +73,7 @@ constexpr int kOffW9 = kOffW7r0 + 256 * 4;               // 3 x 128 floats
 constexpr int kOffMisc = kOffW9 + 3 * 128 * 4;           // b7[0], b9[0..2], c2f weights [16]
 constexpr int kOffPart = kOffMisc + 32 * 4;              // 2 x 128 x 4 floats: cross-warp partial dots
 constexpr int kOffBar = kOffPart + 2 * 128 * 4 * 4;      // mbarriers
-constexpr int kNumBars = 2 * kStages + 5 + 4;
+constexpr int kNumBars = 3 * kStages + 5 + 4;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget exceeded");
 
@@ -105,6 +106,7 @@ struct FwdParams {
   int S;
   int num_tiles;
   int passes;              // 3 (compensated) or 1
+  int ncopies;             // replicas of the packed weight stream
   int save;                // dump A-operand images
   Images img;
 };
@@ -146,6 +148,7 @@ struct PackParams {
 template <bool kF16>
 __global__ void pack_weights_kernel(PackParams pp) {
   int chunk = blockIdx.x;
+  pp.packed += (size_t)blockIdx.y * kChunksPerTile * kChunkBytes;   // replica index (spreads the L2 hot spot)
   int l = 0, base = 0;
   for (;; ++l) {
     int n = layer_nkb(l) * layer_nh(l) * 2;
@@ -279,7 +282,7 @@ __device__ __forceinline__ void split_store32(const float (&f)[32], int row, int
 // ------------------------------------------------------------------------------------------------
 struct ChainSmem {
   uint8_t* base;
-  uint64_t *w_full, *w_empty, *a_ready, *d_full, *d_empty;
+  uint64_t *w_full, *w_empty, *a_ready, *d_full, *d_empty, *w_peer;
   uint32_t* tmem_slot;
 };
 
@@ -292,15 +295,92 @@ __device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem) {
   s.a_ready = bars + 2 * kStages;
   s.d_full = s.a_ready + 5;
   s.d_empty = s.d_full + 2;
+  s.w_peer = s.d_empty + 2;
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   return s;
 }
 
-__device__ __forceinline__ void chain_init_barriers(const ChainSmem& s) {
-  for (int i = 0; i < kStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); }
-  for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps);
-  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], 1); mbar_init(&s.d_empty[i], kEpiWarps); }
+// ncta = 1: stand-alone CTA;  ncta = 2: CTA pair -- the leader's a_ready / d_empty collect the epilogue warps of
+// BOTH CTAs, w_peer[s] tells the leader that the peer's half of weight stage s has landed
+__device__ __forceinline__ void chain_init_barriers(const ChainSmem& s, int ncta = 1) {
+  for (int i = 0; i < kStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); mbar_init(&s.w_peer[i], 1); }
+  for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps * ncta);
+  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], 1); mbar_init(&s.d_empty[i], kEpiWarps * ncta); }
   fence_barrier_init();
+}
+
+// epilogue-warp arrival on a barrier owned by the leader CTA of a pair
+template <bool kPair>
+__device__ __forceinline__ void chain_arrive(uint64_t* bar, uint32_t rank) {
+  if (!kPair || rank == 0) mbar_arrive(bar);
+  else mbar_arrive_cluster(map_to_cta(bar, 0));
+}
+
+// ---- CTA-pair variants of the producer / issuer.  Weight stream of CTA `rank`: the chunks of its N half
+// (nh = rank); the 128-wide head layer splits its single chunk into two 64-row halves.
+//   fwd chunk index = base(l) + (kbi * nh_cnt + nh) * 2 + part ;  bwd = base(bl) + (kbi * 2 + nh) * 2 + part
+__device__ __forceinline__ int fwd_chunk_base(int l) {
+  int b = 0;
+  for (int i = 0; i < l; ++i) b += layer_nkb(i) * layer_nh(i) * 2;
+  return b;
+}
+__device__ __forceinline__ int bwd_chunk_base(int bl) {
+  int b = 0;
+  for (int i = 0; i < bl; ++i) b += bwd_nkb(i) * 4;
+  return b;
+}
+
+// one thread per CTA; `forward_only` = false: the peer's second thread runs the same loop in "forward the
+// completion to the leader" mode instead of issuing copies
+template <bool kBwd>
+__device__ __forceinline__ void pair_weight_loop(const ChainSmem& s, const uint8_t* packed, int my_pairs, int passes,
+                                                 uint32_t rank, bool relay) {
+  uint32_t stage = 0, phase = 0;
+  const int nl = kBwd ? kNumBwdLayers : kNumLayers;
+  for (int it = 0; it < my_pairs; ++it) {
+    for (int l = 0; l < nl; ++l) {
+      const int nkb = kBwd ? bwd_nkb(l) : layer_nkb(l);
+      const bool half = !kBwd && l == 8;      // N = 128: 64 rows per CTA
+      const int base = kBwd ? bwd_chunk_base(l) : fwd_chunk_base(l);
+      for (int kbi = 0; kbi < nkb; ++kbi) {
+        for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
+          if (relay) {
+            mbar_wait(&s.w_full[stage], phase);
+            mbar_arrive_cluster(map_to_cta(&s.w_peer[stage], 0));
+          } else {
+            const int chunk = half ? base + kbi * 2 + part : base + (kbi * 2 + (int)rank) * 2 + part;
+            const uint32_t bytes = half ? kChunkBytes / 2 : kChunkBytes;
+            const uint8_t* src = packed + (size_t)chunk * kChunkBytes + (half ? rank * (kChunkBytes / 2) : 0);
+            mbar_wait(&s.w_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&s.w_full[stage], bytes);
+            bulk_g2s(s.base + kOffRing + stage * kChunkBytes, src, bytes, &s.w_full[stage]);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  }
+}
+
+// leader: all MMAs of one K block (both passes), M = 256 across the pair, N = `n` columns
+__device__ __forceinline__ void pair_issue_block(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
+                                                 uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes) {
+  const uint32_t ring_addr = smem_u32(s.base + kOffRing);
+  for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
+    mbar_wait(&s.w_full[stage], phase);
+    mbar_wait_cluster(&s.w_peer[stage], phase);
+    tc_fence_after();
+    const uint32_t b_addr = ring_addr + stage * kChunkBytes;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t db = make_smem_desc(b_addr + ks * 32);
+      const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
+      umma_ss2(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
+      if (part == 0 && passes != 1) umma_ss2(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+    }
+    umma_commit2(&s.w_empty[stage]);
+    if (++stage == kStages) { stage = 0; phase ^= 1; }
+  }
 }
 
 // weight producer: one thread streams `nchunks` 16 KB chunks per tile through the ring
@@ -341,7 +421,10 @@ __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& 
 // ------------------------------------------------------------------------------------------------
 // the fused forward kernel
 // ------------------------------------------------------------------------------------------------
-template <bool kF16>
+// kPair: launched as clusters of 2 CTAs; each CTA keeps its own 128-row tile (A operand, accumulator lanes,
+// epilogue) but the pair's leader issues ONE tcgen05.mma.cta_group::2 (M = 256) per step with the B operand
+// split across the two SMs, which halves the weight bytes every SM has to pull per unit of tensor work.
+template <bool kF16, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -366,23 +449,65 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
     s_misc[1] = p.b9[0]; s_misc[2] = p.b9[1]; s_misc[3] = p.b9[2];
   }
   if (tid < 16) s_misc[8 + tid] = tid < kL ? band_weight(p.c2f, kL, tid) : 0.f;
-  if (tid == 32) chain_init_barriers(cs);
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint8_t* my_packed = p.packed + (size_t)((kPair ? blockIdx.x / 2 : blockIdx.x) % p.ncopies) * kChunksPerTile * kChunkBytes;
+  if (tid == 32) chain_init_barriers(cs, kPair ? 2 : 1);
+  if (kPair) cluster_sync_all();     // barrier inits of both CTAs visible before any remote arrive / multicast commit
   if (warp == 1) {
-    tmem_alloc(cs.tmem_slot, 512);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc2(cs.tmem_slot, 512); tmem_relinquish2(); }
+    else { tmem_alloc(cs.tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *cs.tmem_slot;
 
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // work items: tiles (stand-alone) or tile pairs (CTA pair: tile = 2 * pair + rank; a missing odd tile is a dummy)
+  const int n_items = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
+  const int n_workers = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
 
   if (warp == 0) {
-    if (lane == 0) chain_producer(cs, p.packed, my_tiles, kChunksPerTile, p.passes == 1);
+    if (lane == 0) {
+      if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
+      else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1);
+    }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    if (kPair && lane == 0 && rank == 1) {
+      pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, true);   // relay "my half landed" to the leader
+    } else if (kPair && lane == 0) {
+      const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
+      uint32_t stage = 0, phase = 0;
+      uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
+      uint32_t d_cnt[2] = {0, 0};
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int buf = l & 1;
+          const uint32_t idesc = make_idesc(256, l == 8 ? 128 : 256, kF16 ? 0 : 1);
+          mbar_wait_cluster(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
+          ++d_cnt[buf];
+          tc_fence_after();
+          const int nkb = layer_nkb(l);
+          for (int kbi = 0; kbi < nkb; ++kbi) {
+            uint32_t a_hi, a_lo;
+            if (kb_is_enc(l, kbi)) {
+              if (l == 0) { mbar_wait_cluster(&cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
+              a_hi = enc_addr; a_lo = enc_addr + kChunkBytes;
+            } else {
+              int a = kb_act_index(l, kbi);
+              mbar_wait_cluster(&cs.a_ready[a], a_cnt[a] & 1);
+              ++a_cnt[a];
+              a_hi = act_addr + a * kChunkBytes; a_lo = act_addr + (4 + a) * kChunkBytes;
+            }
+            tc_fence_after();
+            pair_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, p.passes);
+          }
+          umma_commit2(&cs.d_full[buf]);
+        }
+      }
+    } else if (!kPair && lane == 0) {
       const uint32_t idesc = make_idesc(128, 128, kF16 ? 0 : 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
       uint32_t stage = 0, phase = 0;
@@ -428,10 +553,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
     const float* wts = s_misc + 8;
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
+      const int tile = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
+      const bool tile_ok = tile < p.num_tiles;                       // false only for the dummy half of an odd pair
       const long long m = (long long)tile * kTileM + row;
-      const bool valid = m < p.M;
+      const bool valid = tile_ok && m < p.M;
       const long long ray = valid ? m / p.S : 0;
+      const bool save = p.save && tile_ok;
 
       // ---------------- positional encoding -> A_enc (internal column order: x y z 0 | (sin,cos) pairs)
       {
@@ -458,10 +585,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
           }
         }
         split_store32<kF16>(vals, row, h * 32, smem + kOffEnc, smem + kOffEnc + kChunkBytes,
-                            p.save ? p.img.at(T_ENC, tile, 0, 0) : nullptr, p.save ? p.img.at(T_ENC, tile, 0, 1) : nullptr);
-        fence_proxy_async_smem();
+                            save ? p.img.at(T_ENC, tile, 0, 0) : nullptr, save ? p.img.at(T_ENC, tile, 0, 1) : nullptr);
+        if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&cs.a_ready[4]);
+        if (lane == 0) chain_arrive<kPair>(&cs.a_ready[4], rank);
       }
 
       // ---------------- layers
@@ -504,21 +631,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
               dot1 = fmaf(f[i], s_w9[128 + col0 + i], dot1);
               dot2 = fmaf(f[i], s_w9[256 + col0 + i], dot2);
             }
-            if (p.save)   // hid image for the 128->3 head's weight gradient and its ReLU mask
+            if (save)   // hid image for the 128->3 head's weight gradient and its ReLU mask
               split_store32<kF16>(f, row, h * 32, nullptr, nullptr, p.img.at(T_HID, tile, j, 0), p.img.at(T_HID, tile, j, 1));
           } else {
             const int tsave = l == 7 ? T_FEAT : T_H0 + l;
             split_store32<kF16>(f, row, h * 32, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes,
-                                p.save ? p.img.at(tsave, tile, j, 0) : nullptr, p.save ? p.img.at(tsave, tile, j, 1) : nullptr);
-            fence_proxy_async_smem();
+                                save ? p.img.at(tsave, tile, j, 0) : nullptr, save ? p.img.at(tsave, tile, j, 1) : nullptr);
+            if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+            if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
           }
         }
         // accumulator drained: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&cs.d_empty[buf]);
+        if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
 
         if (l == 6 || l == 8) {
           // combine the two column halves of each row (warps q and q+4) through shared memory
@@ -546,7 +673,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (kPair) cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  if (warp == 1) {
+    if (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -570,6 +700,7 @@ __device__ __forceinline__ uint32_t load_relu_mask(const uint8_t* img_hi, int ro
   return mask;
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -580,21 +711,54 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
 
   for (int i = tid; i < 256; i += kThreads) s_w7r0[i] = p.w7[i];
   for (int i = tid; i < 3 * 128; i += kThreads) s_w9[i] = p.w9[i];
-  if (tid == 32) chain_init_barriers(cs);
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  if (tid == 32) chain_init_barriers(cs, kPair ? 2 : 1);
+  if (kPair) cluster_sync_all();
   if (warp == 1) {
-    tmem_alloc(cs.tmem_slot, 512);
-    tmem_relinquish();
+    if (kPair) { tmem_alloc2(cs.tmem_slot, 512); tmem_relinquish2(); }
+    else { tmem_alloc(cs.tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *cs.tmem_slot;
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_items = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
+  const int n_workers = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
 
   if (warp == 0) {
-    if (lane == 0) chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false);
-  } else if (warp == 1) {
     if (lane == 0) {
+      if (kPair) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false);
+      else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false);
+    }
+  } else if (warp == 1) {
+    if (kPair && lane == 0 && rank == 1) {
+      pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, true);
+    } else if (kPair && lane == 0) {
+      const uint32_t idesc = make_idesc(256, 256, 1);
+      const uint32_t act_addr = smem_u32(smem + kOffAct);
+      uint32_t stage = 0, phase = 0;
+      uint32_t a_cnt[4] = {0, 0, 0, 0};
+      uint32_t d_cnt[2] = {0, 0};
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int bl = 0; bl < kNumBwdLayers; ++bl) {
+          const int buf = bl & 1;
+          mbar_wait_cluster(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
+          ++d_cnt[buf];
+          tc_fence_after();
+          const int nkb = bwd_nkb(bl);
+          for (int kbi = 0; kbi < nkb; ++kbi) {
+            mbar_wait_cluster(&cs.a_ready[kbi], a_cnt[kbi] & 1);
+            ++a_cnt[kbi];
+            tc_fence_after();
+            pair_issue_block(cs, stage, phase, act_addr + kbi * kChunkBytes, act_addr + (4 + kbi) * kChunkBytes,
+                             tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, 3);
+          }
+          umma_commit2(&cs.d_full[buf]);
+        }
+      }
+    } else if (!kPair && lane == 0) {
       const uint32_t idesc = make_idesc(128, 128, 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct);
       uint32_t stage = 0, phase = 0;
@@ -631,9 +795,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
     uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const long long m = (long long)tile * kTileM + row;
-      const bool valid = m < p.M;
+      const int tile_raw = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
+      const bool tile_ok = tile_raw < p.num_tiles;                   // false only for the dummy half of an odd pair
+      const int tile = tile_ok ? tile_raw : 0;                       // dummy: read tile 0's images, write nothing
+      const long long m = (long long)tile_raw * kTileM + row;
+      const bool valid = tile_ok && m < p.M;
 
       // ---------------- head: g_pre = d_rgb * c (1 - c); g_raw = d_sigma * (1 - e^-sigma) [= sigmoid(z)];
       //                  g_hid = (hid > 0) * (g_pre . W9)  -> A blocks 0, 1
@@ -660,10 +826,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           f[i] = ((mask >> i) & 1u) ? g : 0.f;
         }
         split_store32<false>(f, row, h * 32, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes,
-                             p.img.at(T_GHID, tile, j, 0), p.img.at(T_GHID, tile, j, 1));
-        fence_proxy_async_smem();
+                             tile_ok ? p.img.at(T_GHID, tile, j, 0) : nullptr, tile_ok ? p.img.at(T_GHID, tile, j, 1) : nullptr);
+        if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+        if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
       }
 
       // ---------------- backward layers
@@ -694,23 +860,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           }
           const bool chain = bl != kNumBwdLayers - 1;   // G0 is only saved, nothing consumes it on-chip
           split_store32<false>(f, row, h * 32, chain ? act_hi + (size_t)j * kChunkBytes : nullptr,
-                               chain ? act_lo + (size_t)j * kChunkBytes : nullptr, p.img.at(t_out, tile, j, 0),
-                               p.img.at(t_out, tile, j, 1));
+                               chain ? act_lo + (size_t)j * kChunkBytes : nullptr,
+                               tile_ok ? p.img.at(t_out, tile, j, 0) : nullptr, tile_ok ? p.img.at(t_out, tile, j, 1) : nullptr);
           if (chain) {
-            fence_proxy_async_smem();
+            if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+            if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&cs.d_empty[buf]);
+        if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (kPair) cluster_sync_all();
+  if (warp == 1) {
+    if (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1264,7 +1433,7 @@ size_t tc_workspace_bytes(const SparfMLP* mlp, int R, int S, int backward, int e
     int nr = std::min(R, bwd_chunk_rays(S));
     return bwd_carve(nullptr, nr, S, true).total;
   }
-  return align_up((size_t)kChunksPerTile * kChunkBytes, 256) + align_up((size_t)R * kHW * sizeof(float), 256) + 256;
+  return align_up((size_t)16 * kChunksPerTile * kChunkBytes, 256) + align_up((size_t)R * kHW * sizeof(float), 256) + 256;
 }
 
 static void fill_pack_params(const SparfMLP* mlp, PackParams& pp, uint8_t* dst) {
@@ -1273,9 +1442,46 @@ static void fill_pack_params(const SparfMLP* mlp, PackParams& pp, uint8_t* dst) 
   pp.packed = dst;
 }
 
+static int weight_copies() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPARF_TC_WCOPIES");
+    v = e ? std::max(1, std::min(16, atoi(e))) : 1;
+  }
+  return v;
+}
+
+// CTA-pair (cta_group::2) variants of the chain kernels: correct and tested, but measured ~10% SLOWER than the
+// stand-alone-CTA kernels on this workload (profiles/r01_notes.md), so they are opt-in: SPARF_TC_PAIRS=1
+static bool use_cta_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPARF_TC_PAIRS");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <typename K, typename P>
+static cudaError_t launch_clustered(K kernel, int grid, int block, size_t smem, cudaStream_t st, const P& params) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int S, const float* origins, const float* dirs,
                           const float* t, const float* noise, float* sigma, float* rgb, const uint8_t* packed,
-                          const float* raybias, const Images* img, cudaStream_t st) {
+                          const float* raybias, const Images* img, cudaStream_t st, int ncopies = 1) {
   FwdParams p;
   p.packed = packed;
   p.raybias = raybias;
@@ -1290,20 +1496,36 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
   p.S = S;
   p.num_tiles = (int)((p.M + kTileM - 1) / kTileM);
   p.passes = passes;
+  p.ncopies = ncopies;
+  cudaError_t rc_launch = cudaSuccess;
   p.save = img != nullptr;
   if (img) p.img = *img; else { for (int i = 0; i < T_COUNT; ++i) p.img.ptr[i] = nullptr; }
   static bool attr_set = false;
   if (!attr_set) {
-    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
-    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
-    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_encgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgSmem + 1024));
     attr_set = true;
   }
-  int grid = std::min(p.num_tiles, num_sms());
-  if (f16) tc_mlp_fwd_kernel<true><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
-  else tc_mlp_fwd_kernel<false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
+  if (use_cta_pairs() && p.num_tiles >= 2) {
+    const int pairs = (p.num_tiles + 1) / 2;
+    const int grid = 2 * std::min(pairs, num_sms() / 2);
+    rc_launch = f16 ? launch_clustered(tc_mlp_fwd_kernel<true, true>, grid, kThreads, kSmemBytes + 1024, st, p)
+                    : launch_clustered(tc_mlp_fwd_kernel<false, true>, grid, kThreads, kSmemBytes + 1024, st, p);
+    if (rc_launch != cudaSuccess) {
+      set_error("cluster launch of tc_mlp_fwd_kernel failed: %s", cudaGetErrorString(rc_launch));
+      return SPARF_ERR_CUDA;
+    }
+  } else {
+    int grid = std::min(p.num_tiles, num_sms());
+    if (f16) tc_mlp_fwd_kernel<true, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
+    else tc_mlp_fwd_kernel<false, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
+  }
   SPARF_CHECK_LAUNCH("tc_mlp_fwd_kernel");
   return SPARF_OK;
 }
@@ -1322,16 +1544,16 @@ int tc_mlp_forward(const SparfMLP* mlp, int engine, int R, int S, const float* o
     return SPARF_ERR_WORKSPACE;
   }
   uint8_t* packed = reinterpret_cast<uint8_t*>(workspace);
-  float* raybias = reinterpret_cast<float*>(packed + align_up((size_t)kChunksPerTile * kChunkBytes, 256));
+  float* raybias = reinterpret_cast<float*>(packed + align_up((size_t)16 * kChunksPerTile * kChunkBytes, 256));
   PackParams pp;
   fill_pack_params(mlp, pp, packed);
-  pack_weights_kernel<true><<<kChunksPerTile, 256, 0, st>>>(pp);
+  pack_weights_kernel<true><<<dim3(kChunksPerTile, weight_copies()), 256, 0, st>>>(pp);
   SPARF_CHECK_LAUNCH("pack_weights_kernel");
   C2F c2f{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
   raybias_kernel<<<ceil_div(R, 4), 512, 0, st>>>(R, dirs, mlp->head_w[0], mlp->head_b[0], c2f, raybias, nullptr);
   SPARF_CHECK_LAUNCH("raybias_kernel");
   return launch_forward(mlp, true, engine == SPARF_ENGINE_TC_1X ? 1 : 3, R, S, origins, dirs, t, noise, sigma, rgb, packed,
-                        raybias, nullptr, st);
+                        raybias, nullptr, st, weight_copies());
 }
 
 // Training forward: same fp16-split arithmetic and outputs as tc_mlp_forward, plus the tape for the backward.
@@ -1457,7 +1679,16 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     bp.g_raw = c.g_raw; bp.g_pre = c.g_pre;
     bp.w7 = mlp->trunk_w[7]; bp.w9 = mlp->head_w[1];
     bp.M = Mc; bp.num_tiles = ntiles; bp.img = img;
-    tc_mlp_dgrad_kernel<<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
+    if (use_cta_pairs() && ntiles >= 2) {
+      const int grid = 2 * std::min((ntiles + 1) / 2, num_sms() / 2);
+      cudaError_t le = launch_clustered(tc_mlp_dgrad_kernel<true>, grid, kThreads, kSmemBytes + 1024, st, bp);
+      if (le != cudaSuccess) {
+        set_error("cluster launch of tc_mlp_dgrad_kernel failed: %s", cudaGetErrorString(le));
+        return SPARF_ERR_CUDA;
+      }
+    } else {
+      tc_mlp_dgrad_kernel<false><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
+    }
     SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
 
     // 3. weight gradients: job table = (layer, slab of row tiles), ~one CTA per SM

@@ -179,3 +179,45 @@ extern "C" int sparf_tc_selftest(const float* A, const float* B, int32_t K, void
   SPARF_CHECK_LAUNCH("selftest_gemm_kernel");
   return SPARF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Micro-benchmark: per-SM throughput of cp.async.bulk global(L2) -> shared as a function of the number of
+// copies in flight and the copy size (sizes the weight ring of the fused kernels).  One CTA per SM streams
+// `iters` chunks round-robin from a `src_bytes` buffer; a chunk slot is re-armed as soon as its copy landed.
+namespace sparf {
+using namespace tc;
+__global__ void __launch_bounds__(32, 1) bulkcopy_probe_kernel(const uint8_t* __restrict__ src, uint32_t src_bytes, int stages,
+                                                               uint32_t chunk, int iters, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bars[16];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t nchunks = src_bytes / chunk;
+    long long t0 = clock64();
+    for (int i = 0; i < iters + stages; ++i) {
+      const int s = i % stages;
+      if (i >= stages) mbar_wait(&bars[s], ((i / stages) - 1) & 1);   // previous copy into this slot landed
+      if (i < iters) {
+        mbar_arrive_expect_tx(&bars[s], chunk);
+        bulk_g2s(smem + (size_t)s * chunk, src + (size_t)((i + blockIdx.x * 7) % nchunks) * chunk, chunk, &bars[s]);
+      }
+    }
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+}
+}  // namespace sparf
+
+extern "C" int sparf_tc_bulkcopy_probe(const void* src, uint32_t src_bytes, int32_t stages, uint32_t chunk, int32_t iters,
+                                       int32_t grid, long long* cycles, sparf_stream_t stream) {
+  SPARF_REQUIRE(stages >= 1 && stages <= 16 && chunk % 16 == 0 && (size_t)stages * chunk <= 200 * 1024, "bulkcopy_probe: bad shape");
+  size_t smem = (size_t)stages * chunk + 1024;
+  SPARF_CHECK_CUDA(cudaFuncSetAttribute(sparf::bulkcopy_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sparf::bulkcopy_probe_kernel<<<grid, 32, smem, (cudaStream_t)stream>>>((const uint8_t*)src, src_bytes, stages, chunk, iters, cycles);
+  SPARF_CHECK_LAUNCH("bulkcopy_probe_kernel");
+  return SPARF_OK;
+}
