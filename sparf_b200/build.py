@@ -52,6 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = sources()
     defines = ["-DSPARF_WITH_TC"] if os.path.exists(os.path.join(CSRC, "mlp_tc.cu")) else []
+    defines += os.environ.get("SPARF_NVCC_DEFINES", "").split()   # e.g. -DSPARF_TC_TRACE (debug builds only)
     cmd = [_nvcc()] + NVCC_FLAGS + defines + ["-I", INCLUDE, "-o", LIB_PATH + ".tmp"] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -51,7 +51,9 @@ constexpr int kTileM = 128;
 constexpr int kStages = 3;
 constexpr int kChunkBytes = 16384;  // one [128 x 64] 16-bit operand block
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // 320
+constexpr int kProducers = kStages;             // one weight-producer warp per ring stage (bulk copies issue
+                                               // serially per warp at ~500 clk each: tools/probe_bulkcopy.py)
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * (kProducers - 1);  // 384: warps 0, 10, 11 produce
 constexpr int kChunksPerTile = 128;     // forward weight chunks per tile
 constexpr int kBwdChunksPerTile = 120;  // backward (transposed) weight chunks per tile
 
@@ -280,6 +282,31 @@ __device__ __forceinline__ void split_store32(const float (&f)[32], int row, int
 // ------------------------------------------------------------------------------------------------
 // shared pieces of the chain kernels
 // ------------------------------------------------------------------------------------------------
+// wait-time accounting of the warp roles (only with -DSPARF_TC_TRACE; see tools/trace_chain.py)
+struct Trace { long long w[4]; long long t0; int n; };
+#ifdef SPARF_TC_TRACE
+__device__ long long g_tc_trace[148 * 4 * 8];
+__device__ long long g_tc_events[512 * 8];   // CTA 0, first 512 weight chunks: producer / issuer timestamps
+__device__ __forceinline__ void trace_begin(Trace& tr) { tr.w[0] = tr.w[1] = tr.w[2] = tr.w[3] = 0; tr.n = 0; tr.t0 = clock64(); }
+__device__ __forceinline__ void trace_event(long long g, int k) {
+  if (blockIdx.x == 0 && g < 512) g_tc_events[g * 8 + k] = clock64();
+}
+__device__ __forceinline__ void twait(Trace& tr, int cat, uint64_t* bar, uint32_t ph) {
+  long long a = clock64(); mbar_wait(bar, ph); tr.w[cat] += clock64() - a;
+}
+__device__ __forceinline__ void trace_end(const Trace& tr, int role) {
+  if (blockIdx.x < 148) {
+    long long* o = g_tc_trace + ((size_t)blockIdx.x * 4 + role) * 8;
+    o[0] = tr.w[0]; o[1] = tr.w[1]; o[2] = tr.w[2]; o[3] = tr.w[3]; o[4] = clock64() - tr.t0;
+  }
+}
+#else
+__device__ __forceinline__ void trace_begin(Trace&) {}
+__device__ __forceinline__ void trace_event(long long, int) {}
+__device__ __forceinline__ void twait(Trace&, int, uint64_t* bar, uint32_t ph) { mbar_wait(bar, ph); }
+__device__ __forceinline__ void trace_end(const Trace&, int) {}
+#endif
+
 struct ChainSmem {
   uint8_t* base;
   uint64_t *w_full, *w_empty, *a_ready, *d_full, *d_empty, *w_peer;
@@ -330,8 +357,8 @@ __device__ __forceinline__ int bwd_chunk_base(int bl) {
   return b;
 }
 
-// one thread per CTA; `forward_only` = false: the peer's second thread runs the same loop in "forward the
-// completion to the leader" mode instead of issuing copies
+// one WARP per CTA (uniform control flow, an elected lane issues); relay = true: the peer's second warp runs the same
+// loop in "forward the completion to the leader" mode instead of issuing copies
 template <bool kBwd>
 __device__ __forceinline__ void pair_weight_loop(const ChainSmem& s, const uint8_t* packed, int my_pairs, int passes,
                                                  uint32_t rank, bool relay) {
@@ -346,15 +373,18 @@ __device__ __forceinline__ void pair_weight_loop(const ChainSmem& s, const uint8
         for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
           if (relay) {
             mbar_wait(&s.w_full[stage], phase);
-            mbar_arrive_cluster(map_to_cta(&s.w_peer[stage], 0));
+            if (elect_one()) mbar_arrive_cluster(map_to_cta(&s.w_peer[stage], 0));
           } else {
             const int chunk = half ? base + kbi * 2 + part : base + (kbi * 2 + (int)rank) * 2 + part;
             const uint32_t bytes = half ? kChunkBytes / 2 : kChunkBytes;
             const uint8_t* src = packed + (size_t)chunk * kChunkBytes + (half ? rank * (kChunkBytes / 2) : 0);
             mbar_wait(&s.w_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&s.w_full[stage], bytes);
-            bulk_g2s(s.base + kOffRing + stage * kChunkBytes, src, bytes, &s.w_full[stage]);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&s.w_full[stage], bytes);
+              bulk_g2s(s.base + kOffRing + stage * kChunkBytes, src, bytes, &s.w_full[stage]);
+            }
           }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -367,53 +397,73 @@ __device__ __forceinline__ void pair_issue_block(const ChainSmem& s, uint32_t& s
                                                  uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes) {
   const uint32_t ring_addr = smem_u32(s.base + kOffRing);
   for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
-    mbar_wait(&s.w_full[stage], phase);
-    mbar_wait_cluster(&s.w_peer[stage], phase);
+    mbar_wait_both(&s.w_full[stage], &s.w_peer[stage], phase);
     tc_fence_after();
     const uint32_t b_addr = ring_addr + stage * kChunkBytes;
+    if (elect_one()) {
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t db = make_smem_desc(b_addr + ks * 32);
-      const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
-      umma_ss2(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
-      if (part == 0 && passes != 1) umma_ss2(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t db = make_smem_desc(b_addr + ks * 32);
+        const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
+        umma_ss2(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
+        if (part == 0 && passes != 1) umma_ss2(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+      }
+      umma_commit2(&s.w_empty[stage]);
     }
-    umma_commit2(&s.w_empty[stage]);
+    __syncwarp();
     if (++stage == kStages) { stage = 0; phase ^= 1; }
   }
 }
 
-// weight producer: one thread streams `nchunks` 16 KB chunks per tile through the ring
+// weight producers: producer `pidx` of `kProducers` (one thread each, in different warps) owns ring stage `pidx`
+// and streams every kProducers-th 16 KB chunk of the per-tile sequence of `nchunks` chunks
 __device__ __forceinline__ void chain_producer(const ChainSmem& s, const uint8_t* packed, int my_tiles, int nchunks,
-                                               bool skip_lo) {
-  uint32_t stage = 0, phase = 0;
-  for (int it = 0; it < my_tiles; ++it) {
-    for (int c = 0; c < nchunks; ++c) {
-      if (skip_lo && (c & 1)) continue;
-      mbar_wait(&s.w_empty[stage], phase ^ 1);
+                                               bool skip_lo, int pidx) {
+  Trace tr; trace_begin(tr);
+  const int n_eff = skip_lo ? nchunks / 2 : nchunks;
+  const long long total = (long long)my_tiles * n_eff;
+  for (long long g = pidx; g < total; g += kProducers) {
+    const int c_eff = (int)(g % n_eff);
+    const int c = skip_lo ? 2 * c_eff : c_eff;
+    const uint32_t stage = (uint32_t)(g % kStages), phase = (uint32_t)((g / kStages) & 1);
+    twait(tr, 0, &s.w_empty[stage], phase ^ 1);
+    if (elect_one()) {
+      trace_event(g, 0);
       mbar_arrive_expect_tx(&s.w_full[stage], kChunkBytes);
       bulk_g2s(s.base + kOffRing + stage * kChunkBytes, packed + (size_t)c * kChunkBytes, kChunkBytes, &s.w_full[stage]);
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      trace_event(g, 1);
     }
+    __syncwarp();
   }
+  if (pidx == 0 && (threadIdx.x & 31) == 0) trace_end(tr, 0);
 }
 
-// one (K block, N half): waits for its weight chunks and issues the MMAs of all passes
+// one (K block, N half): waits for its weight chunks and issues the MMAs of all passes.  Called by the WHOLE issuer
+// warp (uniform control flow and operands); one elected lane issues.
 __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
-                                                  uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes) {
+                                                  uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes,
+                                                  Trace& tr) {
   const uint32_t ring_addr = smem_u32(s.base + kOffRing);
   for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
-    mbar_wait(&s.w_full[stage], phase);
+    trace_event(tr.n, 2);
+    twait(tr, 2, &s.w_full[stage], phase);
+    trace_event(tr.n, 3);
     tc_fence_after();
     const uint32_t b_addr = ring_addr + stage * kChunkBytes;
+    if (elect_one()) {
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t db = make_smem_desc(b_addr + ks * 32);
-      const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
-      umma_ss(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
-      if (part == 0 && passes != 1) umma_ss(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t db = make_smem_desc(b_addr + ks * 32);
+        const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
+        umma_ss(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
+        if (part == 0 && passes != 1) umma_ss(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+      }
+      trace_event(tr.n, 4);
+      umma_commit(&s.w_empty[stage]);   // frees the ring slot when these MMAs have read it
+      trace_event(tr.n, 5);
     }
-    umma_commit(&s.w_empty[stage]);   // frees the ring slot when these MMAs have read it
+    __syncwarp();
+    ++tr.n;
     if (++stage == kStages) { stage = 0; phase ^= 1; }
   }
 }
@@ -460,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *cs.tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *cs.tmem_slot, 0);   // warp-uniform for the compiler
 
   // work items: tiles (stand-alone) or tile pairs (CTA pair: tile = 2 * pair + rank; a missing odd tile is a dummy)
   const int n_items = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
@@ -468,16 +518,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
   const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
-      else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1);
-    }
+  if (warp == 0 || warp >= 2 + kEpiWarps) {
+    const int pidx = warp == 0 ? 0 : warp - (1 + kEpiWarps);
+    if (kPair) { if (pidx == 0) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false); }
+    else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1, pidx);   // whole warp, one elected lane issues
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (kPair && lane == 0 && rank == 1) {
+    if (kPair && rank == 1) {
       pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, true);   // relay "my half landed" to the leader
-    } else if (kPair && lane == 0) {
+    } else if (kPair) {
       const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
       uint32_t stage = 0, phase = 0;
       uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
@@ -504,41 +553,45 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
             tc_fence_after();
             pair_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, p.passes);
           }
-          umma_commit2(&cs.d_full[buf]);
+          if (elect_one()) umma_commit2(&cs.d_full[buf]);
+          __syncwarp();
         }
       }
-    } else if (!kPair && lane == 0) {
+    } else if (!kPair) {
       const uint32_t idesc = make_idesc(128, 128, kF16 ? 0 : 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
       uint32_t stage = 0, phase = 0;
       uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
       uint32_t d_cnt[2] = {0, 0};
+      Trace tr; trace_begin(tr);
       for (int it = 0; it < my_tiles; ++it) {
         for (int l = 0; l < kNumLayers; ++l) {
           const int buf = l & 1;
-          mbar_wait(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);   // epilogue of the previous user of this accumulator
+          twait(tr, 0, &cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);   // epilogue of the previous user of this accumulator
           ++d_cnt[buf];
           tc_fence_after();
           const int nkb = layer_nkb(l), nh_cnt = layer_nh(l);
           for (int kbi = 0; kbi < nkb; ++kbi) {
             uint32_t a_hi, a_lo;
             if (kb_is_enc(l, kbi)) {
-              if (l == 0) { mbar_wait(&cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
+              if (l == 0) { twait(tr, 1, &cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
               a_hi = enc_addr; a_lo = enc_addr + kChunkBytes;
             } else {
               int a = kb_act_index(l, kbi);
-              mbar_wait(&cs.a_ready[a], a_cnt[a] & 1);
+              twait(tr, 1, &cs.a_ready[a], a_cnt[a] & 1);
               ++a_cnt[a];
               a_hi = act_addr + a * kChunkBytes; a_lo = act_addr + (4 + a) * kChunkBytes;
             }
             tc_fence_after();
             for (int nh = 0; nh < nh_cnt; ++nh)
               chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
-                                kbi == 0, p.passes);
+                                kbi == 0, p.passes, tr);
           }
-          umma_commit(&cs.d_full[buf]);            // accumulator of layer l complete
+          if (elect_one()) umma_commit(&cs.d_full[buf]);            // accumulator of layer l complete
+          __syncwarp();
         }
       }
+      if (lane == 0) trace_end(tr, 1);
     }
   } else {
     // ============================== epilogue warps ==============================
@@ -551,6 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
     uint8_t* act_hi = smem + kOffAct;
     uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
     const float* wts = s_misc + 8;
+    Trace tr; trace_begin(tr);
 
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
@@ -594,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
       // ---------------- layers
       for (int l = 0; l < kNumLayers; ++l) {
         const int buf = l & 1;
-        mbar_wait(&cs.d_full[buf], d_cnt[buf] & 1);
+        twait(tr, 0, &cs.d_full[buf], d_cnt[buf] & 1);
         ++d_cnt[buf];
         tc_fence_after();
         const int nchunk = l == 8 ? 2 : 4;
@@ -668,6 +722,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
         }
       }
     }
+    if (lane == 0 && (e == 0 || e == 7)) trace_end(tr, e == 0 ? 2 : 3);
   }
 
   // ---- teardown
@@ -721,21 +776,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *cs.tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *cs.tmem_slot, 0);
   const int n_items = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
   const int n_workers = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
   const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
   const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      if (kPair) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false);
-      else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false);
-    }
+  if (warp == 0 || warp >= 2 + kEpiWarps) {
+    const int pidx = warp == 0 ? 0 : warp - (1 + kEpiWarps);
+    if (kPair) { if (pidx == 0) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false); }
+    else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false, pidx);
   } else if (warp == 1) {
-    if (kPair && lane == 0 && rank == 1) {
+    if (kPair && rank == 1) {
       pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, true);
-    } else if (kPair && lane == 0) {
+    } else if (kPair) {
       const uint32_t idesc = make_idesc(256, 256, 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct);
       uint32_t stage = 0, phase = 0;
@@ -755,34 +809,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             pair_issue_block(cs, stage, phase, act_addr + kbi * kChunkBytes, act_addr + (4 + kbi) * kChunkBytes,
                              tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, 3);
           }
-          umma_commit2(&cs.d_full[buf]);
+          if (elect_one()) umma_commit2(&cs.d_full[buf]);
+          __syncwarp();
         }
       }
-    } else if (!kPair && lane == 0) {
+    } else if (!kPair) {
       const uint32_t idesc = make_idesc(128, 128, 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct);
       uint32_t stage = 0, phase = 0;
       uint32_t a_cnt[4] = {0, 0, 0, 0};
       uint32_t d_cnt[2] = {0, 0};
+      Trace tr; trace_begin(tr);
       for (int it = 0; it < my_tiles; ++it) {
         for (int bl = 0; bl < kNumBwdLayers; ++bl) {
           const int buf = bl & 1;
-          mbar_wait(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
+          twait(tr, 0, &cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
           ++d_cnt[buf];
           tc_fence_after();
           const int nkb = bwd_nkb(bl);
           for (int kbi = 0; kbi < nkb; ++kbi) {
-            mbar_wait(&cs.a_ready[kbi], a_cnt[kbi] & 1);
+            twait(tr, 1, &cs.a_ready[kbi], a_cnt[kbi] & 1);
             ++a_cnt[kbi];
             tc_fence_after();
             const uint32_t a_hi = act_addr + kbi * kChunkBytes, a_lo = act_addr + (4 + kbi) * kChunkBytes;
             for (int nh = 0; nh < 2; ++nh)
               chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
-                                kbi == 0, 3);
+                                kbi == 0, 3, tr);
           }
-          umma_commit(&cs.d_full[buf]);
+          if (elect_one()) umma_commit(&cs.d_full[buf]);
+          __syncwarp();
         }
       }
+      if (lane == 0) trace_end(tr, 1);
     }
   } else {
     const int e = warp - 2;
@@ -793,6 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
     uint32_t d_cnt[2] = {0, 0};
     uint8_t* act_hi = smem + kOffAct;
     uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
+    Trace tr; trace_begin(tr);
 
     for (int it = 0; it < my_tiles; ++it) {
       const int tile_raw = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
@@ -841,7 +900,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         uint32_t masks[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) masks[j] = load_relu_mask(p.img.at(t_mask, tile, j, 0), row, h * 32);
-        mbar_wait(&cs.d_full[buf], d_cnt[buf] & 1);
+        twait(tr, 0, &cs.d_full[buf], d_cnt[buf] & 1);
         ++d_cnt[buf];
         tc_fence_after();
 #pragma unroll 1
@@ -873,6 +932,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
       }
     }
+    if (lane == 0 && (e == 0 || e == 7)) trace_end(tr, e == 0 ? 2 : 3);
   }
   tc_fence_before();
   __syncthreads();
@@ -1462,6 +1522,35 @@ static bool use_cta_pairs() {
   return v == 1;
 }
 
+#ifdef SPARF_TC_TRACE
+static void trace_dump(const char* what) {
+  static long long h[148 * 4 * 8];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_tc_trace, sizeof(h));
+  const char* roles[4] = {"producer0 (w0 = ring slot free)", "mma issuer (w0 = acc free, w1 = A ready, w2 = weights landed)",
+                          "epilogue warp 0 (w0 = acc full)", "epilogue warp 7 (w0 = acc full)"};
+  fprintf(stderr, "[tc trace] %s, mean over CTAs 0..147 (clocks)\n", what);
+  for (int r = 0; r < 4; ++r) {
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int b = 0; b < 148; ++b)
+      for (int k = 0; k < 5; ++k) a[k] += (double)h[((size_t)b * 4 + r) * 8 + k] / 148.0;
+    fprintf(stderr, "  %-70s total %9.0f  w0 %9.0f  w1 %9.0f  w2 %9.0f\n", roles[r], a[4], a[0], a[1], a[2]);
+  }
+  if (getenv("SPARF_TC_TRACE_EVENTS")) {
+    static long long ev[512 * 8];
+    cudaMemcpyFromSymbol(ev, g_tc_events, sizeof(ev));
+    const long long t0 = ev[1];
+    fprintf(stderr, "  chunk: slot-free  copy-issued | issuer: at-wait  weights-seen  mmas-issued  committed   (clocks since first copy)\n");
+    for (int g = 128; g < 200; ++g)
+      fprintf(stderr, "  %4d: %9lld %9lld | %9lld %9lld %9lld %9lld\n", g, ev[g * 8] - t0, ev[g * 8 + 1] - t0, ev[g * 8 + 2] - t0,
+              ev[g * 8 + 3] - t0, ev[g * 8 + 4] - t0, ev[g * 8 + 5] - t0);
+  }
+}
+#define TRACE_DUMP(what) trace_dump(what)
+#else
+#define TRACE_DUMP(what) ((void)0)
+#endif
+
 template <typename K, typename P>
 static cudaError_t launch_clustered(K kernel, int grid, int block, size_t smem, cudaStream_t st, const P& params) {
   cudaLaunchConfig_t cfg = {};
@@ -1525,6 +1614,7 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
     int grid = std::min(p.num_tiles, num_sms());
     if (f16) tc_mlp_fwd_kernel<true, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
     else tc_mlp_fwd_kernel<false, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
+    TRACE_DUMP(p.save ? "forward (tape)" : (f16 ? "forward f16" : "forward bf16"));
   }
   SPARF_CHECK_LAUNCH("tc_mlp_fwd_kernel");
   return SPARF_OK;
@@ -1688,6 +1778,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       }
     } else {
       tc_mlp_dgrad_kernel<false><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
+      TRACE_DUMP("dgrad");
     }
     SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
 

@@ -101,6 +101,28 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+// wait on two LOCAL barriers of the same parity at once (own weights landed + peer's "landed" relay): both polls are
+// in flight together, so the pair costs one barrier round trip instead of two
+__device__ __forceinline__ void mbar_wait_both(uint64_t* bar_cta, uint64_t* bar_cluster, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %3;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 q, [%2], %3;\n\t"
+        "and.pred p, p, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar_cta)), "r"(smem_u32(bar_cluster)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 26)) {
+      printf("sparf tc: paired mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {   // same warp id in both CTAs
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                : "memory");
@@ -150,6 +172,14 @@ __device__ __forceinline__ void tmem_relinquish() {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp that allocated
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// true in exactly one lane of a converged warp.  The MMA / bulk-copy issue loops run warp-uniform and predicate only
+// the issuing instruction on this, so their operands (descriptors, addresses) stay in uniform registers; under a
+// plain `if (lane == 0)` the compiler emits an ELECT + 5x R2UR "waterfall" loop around every tcgen05.mma.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -186,7 +186,7 @@ extern "C" int sparf_tc_selftest(const float* A, const float* B, int32_t K, void
 // `iters` chunks round-robin from a `src_bytes` buffer; a chunk slot is re-armed as soon as its copy landed.
 namespace sparf {
 using namespace tc;
-__global__ void __launch_bounds__(32, 1) bulkcopy_probe_kernel(const uint8_t* __restrict__ src, uint32_t src_bytes, int stages,
+__global__ void __launch_bounds__(128, 1) bulkcopy_probe_kernel(const uint8_t* __restrict__ src, uint32_t src_bytes, int stages,
                                                                uint32_t chunk, int iters, long long* __restrict__ cycles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -196,18 +196,30 @@ __global__ void __launch_bounds__(32, 1) bulkcopy_probe_kernel(const uint8_t* __
     fence_barrier_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  // issuers: lane 0 of each of the first `nissue` warps (encoded in the high bits of `iters`); issuer w owns the
+  // slots s with s % nissue == w
+  const int nissue = max(1, (iters >> 24) & 15);
+  const int lanes_code = (iters >> 28) & 15;
+  const int nlanes = lanes_code == 0 ? 1 : lanes_code * 4;     // lanes per issuer warp, each copies chunk / nlanes bytes
+  iters &= 0xFFFFFF;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (w < nissue) {
     const uint32_t nchunks = src_bytes / chunk;
+    const uint32_t piece = chunk / nlanes;
+    const int active = chunk / piece;
     long long t0 = clock64();
-    for (int i = 0; i < iters + stages; ++i) {
+    for (int i = w; i < iters + stages; i += nissue) {
       const int s = i % stages;
       if (i >= stages) mbar_wait(&bars[s], ((i / stages) - 1) & 1);   // previous copy into this slot landed
       if (i < iters) {
-        mbar_arrive_expect_tx(&bars[s], chunk);
-        bulk_g2s(smem + (size_t)s * chunk, src + (size_t)((i + blockIdx.x * 7) % nchunks) * chunk, chunk, &bars[s]);
+        if (lane == 0) mbar_arrive_expect_tx(&bars[s], chunk);
+        __syncwarp();
+        if (lane < active)
+          bulk_g2s(smem + (size_t)s * chunk + lane * piece, src + (size_t)((i + blockIdx.x * 7) % nchunks) * chunk + lane * piece,
+                   piece, &bars[s]);
       }
     }
-    cycles[blockIdx.x] = clock64() - t0;
+    if (w == 0 && lane == 0) cycles[blockIdx.x] = clock64() - t0;
   }
 }
 }  // namespace sparf
@@ -217,7 +229,7 @@ extern "C" int sparf_tc_bulkcopy_probe(const void* src, uint32_t src_bytes, int3
   SPARF_REQUIRE(stages >= 1 && stages <= 16 && chunk % 16 == 0 && (size_t)stages * chunk <= 200 * 1024, "bulkcopy_probe: bad shape");
   size_t smem = (size_t)stages * chunk + 1024;
   SPARF_CHECK_CUDA(cudaFuncSetAttribute(sparf::bulkcopy_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sparf::bulkcopy_probe_kernel<<<grid, 32, smem, (cudaStream_t)stream>>>((const uint8_t*)src, src_bytes, stages, chunk, iters, cycles);
+  sparf::bulkcopy_probe_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>((const uint8_t*)src, src_bytes, stages, chunk, iters, cycles);
   SPARF_CHECK_LAUNCH("bulkcopy_probe_kernel");
   return SPARF_OK;
 }

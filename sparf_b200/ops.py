@@ -141,7 +141,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 class MLPFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, spec: MLPSpec, engine: int, origins, dirs, t, noise, progress, *params):
+    def forward(ctx, spec: MLPSpec, engine: int, grad_mode: bool, origins, dirs, t, noise, progress, *params):
         L = _lib.lib()
         origins, dirs, t = _f32c(origins), _f32c(dirs), _f32c(t)
         R, S = t.shape
@@ -154,7 +154,8 @@ class MLPFunction(torch.autograd.Function):
         ws = _workspace(nbytes, t.device)
         # Training forward: when a gradient will be asked for and the engine offers it, keep a "tape" (the
         # per-layer operand images) so that the backward skips the forward recompute.
-        wants_grad = any(ctx.needs_input_grad[i] for i in (2, 3)) or any(ctx.needs_input_grad[7:])
+        # (grad_mode: autograd is recording at the call site -- under torch.no_grad() nothing is kept)
+        wants_grad = grad_mode and (any(ctx.needs_input_grad[i] for i in (3, 4)) or any(ctx.needs_input_grad[8:]))
         tape_bytes = L.sparf_mlp_tape_bytes(ctypes.byref(m), engine, R, S) if (wants_grad and USE_TAPE[0]) else 0
         ctx.tape = None
         with _timed("mlp_forward"):
@@ -200,7 +201,7 @@ class MLPFunction(torch.autograd.Function):
                 grads.append(flat[o:o + n].view(p.shape))
                 o += n
         gs = spec.grad_struct(grads)
-        need_o, need_d = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        need_o, need_d = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         d_o = torch.zeros_like(origins) if (need_o or need_d) else None
         d_d = torch.zeros_like(dirs) if (need_o or need_d) else None
         nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 1, ctx.engine)
@@ -218,14 +219,14 @@ class MLPFunction(torch.autograd.Function):
                                            _ptr(d_d), _ptr(ws), ws.numel(), _stream()), "mlp_backward")
         if inplace:
             grads = [None] * len(grads)
-        return (None, None, d_o if need_o else None, d_d if need_d else None, None, None, None, *grads)
+        return (None, None, None, d_o if need_o else None, d_d if need_d else None, None, None, None, *grads)
 
 
 def mlp_forward(spec: MLPSpec, origins, dirs, t, params: Sequence[torch.Tensor], *, noise=None, progress=None,
                 engine: Optional[int] = None):
     """origins/dirs [R,3], t [R,S] -> (sigma [R,S], rgb [R,S,3]); differentiable w.r.t. origins, dirs, params."""
     eng = get_engine() if engine is None else engine
-    return MLPFunction.apply(spec, eng, origins, dirs, t, noise, progress, *params)
+    return MLPFunction.apply(spec, eng, torch.is_grad_enabled(), origins, dirs, t, noise, progress, *params)
 
 
 # ------------------------------------------------------------------------------------------------
