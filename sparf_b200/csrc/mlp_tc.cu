@@ -48,12 +48,19 @@ constexpr int kEv = 27;
 constexpr int kNumLayers = 9;    // forward tensor-core layers: trunk 0..7 + head 0
 constexpr int kNumBwdLayers = 8; // backward tensor-core layers
 constexpr int kTileM = 128;
-constexpr int kStages = 3;
+constexpr int kStages = 3;         // weight-ring stages of the forward kernel
+constexpr int kBwdStages = 5;      // ... of the dgrad kernel, whose ring also takes the two encoder blocks it does not use
+constexpr int kMaxStages = 6;
 constexpr int kChunkBytes = 16384;  // one [128 x 64] 16-bit operand block
-constexpr int kEpiWarps = 8;
-constexpr int kProducers = kStages;             // one weight-producer warp per ring stage (bulk copies issue
-                                               // serially per warp at ~500 clk each: tools/probe_bulkcopy.py)
-constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * (kProducers - 1);  // 384: warps 0, 10, 11 produce
+constexpr int kEpiWarps = 16;       // 4 TMEM lane quadrants x 4 column quarters of every 64-column block
+constexpr int kEpiCols = 16;        // columns per epilogue warp and block
+constexpr int kProducers = 1;                   // weight-producer warps (warp 0, then the warps after the epilogue warps)
+constexpr int kIssuers = 2;                     // MMA-issuing warps of a stand-alone CTA: warp 1 owns accumulator columns
+                                               // 0..127 (N half 0), the warp after the epilogue warps owns N half 1.
+                                               // One warp alone spends ~800 clk of dependent uniform-datapath work per
+                                               // 16 KB weight chunk, more than the chunk's 256..512 clk of tensor work.
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * (kIssuers - 1) + 32;  // 640; the last warp (dgrad) streams the
+                                               // gradient images from shared memory to HBM with bulk copies
 constexpr int kChunksPerTile = 128;     // forward weight chunks per tile
 constexpr int kBwdChunksPerTile = 120;  // backward (transposed) weight chunks per tile
 
@@ -73,9 +80,9 @@ constexpr int kOffBias = kOffRing + kStages * kChunkBytes;   // 8 x 256 floats (
 constexpr int kOffW7r0 = kOffBias + 8 * 256 * 4;         // 256 floats: density row of the last trunk layer
 constexpr int kOffW9 = kOffW7r0 + 256 * 4;               // 3 x 128 floats
 constexpr int kOffMisc = kOffW9 + 3 * 128 * 4;           // b7[0], b9[0..2], c2f weights [16]
-constexpr int kOffPart = kOffMisc + 32 * 4;              // 2 x 128 x 4 floats: cross-warp partial dots
-constexpr int kOffBar = kOffPart + 2 * 128 * 4 * 4;      // mbarriers
-constexpr int kNumBars = 3 * kStages + 5 + 4;
+constexpr int kOffPart = kOffMisc + 32 * 4;              // 3 x 128 x 4 floats: partial dots of column quarters 1..3
+constexpr int kOffBar = kOffPart + 3 * 128 * 4 * 4;      // mbarriers
+constexpr int kNumBars = 3 * kMaxStages + 5 + 4 + 8;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget exceeded");
 
@@ -83,10 +90,18 @@ static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget exceeded");
 enum { T_ENC = 0, T_H0 = 1, T_FEAT = 8, T_HID = 9, T_GHID = 10, T_G7F = 11, T_G6 = 12, T_G0 = 18, T_COUNT = 19 };
 __host__ __device__ constexpr int tensor_nblk(int t) { return t == T_ENC ? 1 : ((t == T_HID || t == T_GHID) ? 2 : 4); }
 __host__ __device__ constexpr int t_g(int l) { return T_G6 + (6 - l); }   // image of dL/dz_l, l = 0..6
+// ReLU masks of the forward activations (what the dgrad chain needs of them): layer 0..6 = h0..h6, 7 = feat, 8 = hid;
+// per (tile, layer, row): 4 x 64 bits, one word per 16-column quarter cq, bit 16 * block + i = column 64 * block + 16 * cq + i
+constexpr int kMaskLayers = 9;
+constexpr size_t kMaskTileBytes = (size_t)kMaskLayers * 128 * 32;
 struct Images {
   uint8_t* ptr[T_COUNT];   // forward tensors (t < T_GHID) may live in a caller-held tape, gradients in the workspace
+  uint8_t* mask;           // forward side
   __host__ __device__ uint8_t* at(int t, int tile, int blk, int part) const {
     return ptr[t] + ((((size_t)tile * tensor_nblk(t)) + blk) * 2 + part) * kChunkBytes;
+  }
+  __host__ __device__ uint2* mask_at(int tile, int layer, int row, int cq) const {
+    return reinterpret_cast<uint2*>(mask + (((size_t)tile * kMaskLayers + layer) * 128 + row) * 32 + cq * 8);
   }
 };
 
@@ -244,38 +259,40 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// split 32 fp32 values of one row into hi/lo words and store them as columns [col0, col0+32) of a
-// [128 x 64] SW128 block in shared memory (and optionally in its HBM image)
+// split 16 fp32 values of one row into hi/lo words and store them as columns [col0, col0+16) of a
+// [128 x 64] SW128 block in shared memory; `save_image` writes the same columns of its HBM image (always bf16 halves:
+// the gradient kernels work on those).  The HBM stores come last so that the caller's proxy fence + arrive, which
+// release the shared-memory copy to the tensor core, do not sit behind them.
+struct Split16 { uint32_t hi[8], lo[8]; };
 template <bool kF16>
-__device__ __forceinline__ void split_store32(const float (&f)[32], int row, int col0, uint8_t* s_hi, uint8_t* s_lo,
-                                              uint8_t* g_hi, uint8_t* g_lo) {
-  uint32_t hi[16], lo[16];
+__device__ __forceinline__ void split16(const float (&f)[16], Split16& o) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) split2<kF16>(f[2 * i], f[2 * i + 1], hi[i], lo[i]);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t off = sw128_offset(row, col0 + c * 8);
-    const uint4 vh = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-    const uint4 vl = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
-    if (s_hi) {
-      *reinterpret_cast<uint4*>(s_hi + off) = vh;
-      *reinterpret_cast<uint4*>(s_lo + off) = vl;
-    }
-    if (g_hi && !kF16) {
-      *reinterpret_cast<uint4*>(g_hi + off) = vh;
-      *reinterpret_cast<uint4*>(g_lo + off) = vl;
-    }
+  for (int i = 0; i < 8; ++i) split2<kF16>(f[2 * i], f[2 * i + 1], o.hi[i], o.lo[i]);
+}
+// same into an HBM image: this thread's 16 columns are one aligned 32-byte sector of the row in each block (the
+// swizzle only permutes its two 16-byte chunks), written with one 256-bit store per block
+__device__ __forceinline__ void st_global_256(uint8_t* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                              uint32_t b1, uint32_t b2, uint32_t b3) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3)
+               : "memory");
+}
+__device__ __forceinline__ void store16_image(const Split16& v, int row, int col0, uint8_t* g_hi, uint8_t* g_lo) {
+  const uint32_t off = sw128_offset(row, col0) & ~31u;
+  if (row & 1) {   // odd rows: the swizzle swaps the two chunks of the sector
+    st_global_256(g_hi + off, v.hi[4], v.hi[5], v.hi[6], v.hi[7], v.hi[0], v.hi[1], v.hi[2], v.hi[3]);
+    st_global_256(g_lo + off, v.lo[4], v.lo[5], v.lo[6], v.lo[7], v.lo[0], v.lo[1], v.lo[2], v.lo[3]);
+  } else {
+    st_global_256(g_hi + off, v.hi[0], v.hi[1], v.hi[2], v.hi[3], v.hi[4], v.hi[5], v.hi[6], v.hi[7]);
+    st_global_256(g_lo + off, v.lo[0], v.lo[1], v.lo[2], v.lo[3], v.lo[4], v.lo[5], v.lo[6], v.lo[7]);
   }
-  if (kF16 && g_hi) {   // the HBM images feed the gradient kernels, which work on bf16 halves
-    uint32_t bh[16], bl[16];
+}
+__device__ __forceinline__ void store16(const Split16& v, int row, int col0, uint8_t* b_hi, uint8_t* b_lo) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) split2<false>(f[2 * i], f[2 * i + 1], bh[i], bl[i]);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t off = sw128_offset(row, col0 + c * 8);
-      *reinterpret_cast<uint4*>(g_hi + off) = make_uint4(bh[4 * c], bh[4 * c + 1], bh[4 * c + 2], bh[4 * c + 3]);
-      *reinterpret_cast<uint4*>(g_lo + off) = make_uint4(bl[4 * c], bl[4 * c + 1], bl[4 * c + 2], bl[4 * c + 3]);
-    }
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t off = sw128_offset(row, col0 + c * 8);
+    *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(v.hi[4 * c], v.hi[4 * c + 1], v.hi[4 * c + 2], v.hi[4 * c + 3]);
+    *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(v.lo[4 * c], v.lo[4 * c + 1], v.lo[4 * c + 2], v.lo[4 * c + 3]);
   }
 }
 
@@ -289,11 +306,15 @@ __device__ long long g_tc_trace[148 * 4 * 8];
 __device__ long long g_tc_events[512 * 8];   // CTA 0, first 512 weight chunks: producer / issuer timestamps
 __device__ __forceinline__ void trace_begin(Trace& tr) { tr.w[0] = tr.w[1] = tr.w[2] = tr.w[3] = 0; tr.n = 0; tr.t0 = clock64(); }
 __device__ __forceinline__ void trace_event(long long g, int k) {
+#ifdef SPARF_TC_TRACE_EVENTS
   if (blockIdx.x == 0 && g < 512) g_tc_events[g * 8 + k] = clock64();
+#endif
 }
 __device__ __forceinline__ void twait(Trace& tr, int cat, uint64_t* bar, uint32_t ph) {
   long long a = clock64(); mbar_wait(bar, ph); tr.w[cat] += clock64() - a;
 }
+__device__ __forceinline__ long long trace_tic() { return clock64(); }
+__device__ __forceinline__ void trace_toc(Trace& tr, int cat, long long t0) { tr.w[cat] += clock64() - t0; }
 __device__ __forceinline__ void trace_end(const Trace& tr, int role) {
   if (blockIdx.x < 148) {
     long long* o = g_tc_trace + ((size_t)blockIdx.x * 4 + role) * 8;
@@ -305,24 +326,33 @@ __device__ __forceinline__ void trace_begin(Trace&) {}
 __device__ __forceinline__ void trace_event(long long, int) {}
 __device__ __forceinline__ void twait(Trace&, int, uint64_t* bar, uint32_t ph) { mbar_wait(bar, ph); }
 __device__ __forceinline__ void trace_end(const Trace&, int) {}
+__device__ __forceinline__ long long trace_tic() { return 0; }
+__device__ __forceinline__ void trace_toc(Trace&, int, long long) {}
 #endif
 
 struct ChainSmem {
   uint8_t* base;
+  uint8_t* ring;           // nstages x 16 KB weight ring
+  int nstages;
   uint64_t *w_full, *w_empty, *a_ready, *d_full, *d_empty, *w_peer;
+  uint64_t *g_ready, *s_free;   // dgrad: block j holds a finished gradient image / has been streamed out
   uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem) {
+__device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem, int ring_off, int nstages) {
   ChainSmem s;
   s.base = smem;
+  s.ring = smem + ring_off;
+  s.nstages = nstages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   s.w_full = bars;
-  s.w_empty = bars + kStages;
-  s.a_ready = bars + 2 * kStages;
+  s.w_empty = bars + kMaxStages;
+  s.a_ready = bars + 2 * kMaxStages;
   s.d_full = s.a_ready + 5;
   s.d_empty = s.d_full + 2;
   s.w_peer = s.d_empty + 2;
+  s.g_ready = s.w_peer + kMaxStages;
+  s.s_free = s.g_ready + 4;
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   return s;
 }
@@ -330,9 +360,11 @@ __device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem) {
 // ncta = 1: stand-alone CTA;  ncta = 2: CTA pair -- the leader's a_ready / d_empty collect the epilogue warps of
 // BOTH CTAs, w_peer[s] tells the leader that the peer's half of weight stage s has landed
 __device__ __forceinline__ void chain_init_barriers(const ChainSmem& s, int ncta = 1) {
-  for (int i = 0; i < kStages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); mbar_init(&s.w_peer[i], 1); }
+  for (int i = 0; i < s.nstages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); mbar_init(&s.w_peer[i], 1); }
   for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps * ncta);
-  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], 1); mbar_init(&s.d_empty[i], kEpiWarps * ncta); }
+  for (int i = 0; i < 4; ++i) { mbar_init(&s.g_ready[i], kEpiWarps); mbar_init(&s.s_free[i], 1); }
+  // d_full: one commit per issuer warp (stand-alone) or the leader's multicast commit (pair)
+  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], ncta == 1 ? kIssuers : 1); mbar_init(&s.d_empty[i], kEpiWarps * ncta); }
   fence_barrier_init();
 }
 
@@ -381,11 +413,11 @@ __device__ __forceinline__ void pair_weight_loop(const ChainSmem& s, const uint8
             mbar_wait(&s.w_empty[stage], phase ^ 1);
             if (elect_one()) {
               mbar_arrive_expect_tx(&s.w_full[stage], bytes);
-              bulk_g2s(s.base + kOffRing + stage * kChunkBytes, src, bytes, &s.w_full[stage]);
+              bulk_g2s(s.ring + stage * kChunkBytes, src, bytes, &s.w_full[stage]);
             }
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -395,7 +427,7 @@ __device__ __forceinline__ void pair_weight_loop(const ChainSmem& s, const uint8
 // leader: all MMAs of one K block (both passes), M = 256 across the pair, N = `n` columns
 __device__ __forceinline__ void pair_issue_block(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
                                                  uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes) {
-  const uint32_t ring_addr = smem_u32(s.base + kOffRing);
+  const uint32_t ring_addr = smem_u32(s.ring);
   for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
     mbar_wait_both(&s.w_full[stage], &s.w_peer[stage], phase);
     tc_fence_after();
@@ -411,7 +443,7 @@ __device__ __forceinline__ void pair_issue_block(const ChainSmem& s, uint32_t& s
       umma_commit2(&s.w_empty[stage]);
     }
     __syncwarp();
-    if (++stage == kStages) { stage = 0; phase ^= 1; }
+    if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
   }
 }
 
@@ -425,12 +457,12 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const uint8_t
   for (long long g = pidx; g < total; g += kProducers) {
     const int c_eff = (int)(g % n_eff);
     const int c = skip_lo ? 2 * c_eff : c_eff;
-    const uint32_t stage = (uint32_t)(g % kStages), phase = (uint32_t)((g / kStages) & 1);
+    const uint32_t stage = (uint32_t)(g % s.nstages), phase = (uint32_t)((g / s.nstages) & 1);
     twait(tr, 0, &s.w_empty[stage], phase ^ 1);
     if (elect_one()) {
       trace_event(g, 0);
       mbar_arrive_expect_tx(&s.w_full[stage], kChunkBytes);
-      bulk_g2s(s.base + kOffRing + stage * kChunkBytes, packed + (size_t)c * kChunkBytes, kChunkBytes, &s.w_full[stage]);
+      bulk_g2s(s.ring + stage * kChunkBytes, packed + (size_t)c * kChunkBytes, kChunkBytes, &s.w_full[stage]);
       trace_event(g, 1);
     }
     __syncwarp();
@@ -442,9 +474,13 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const uint8_t
 // warp (uniform control flow and operands); one elected lane issues.
 __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
                                                   uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes,
-                                                  Trace& tr) {
-  const uint32_t ring_addr = smem_u32(s.base + kOffRing);
+                                                  bool mine, Trace& tr) {
+  const uint32_t ring_addr = smem_u32(s.ring);
   for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
+    if (!mine) {   // the other issuer warp's chunk: only step the ring position
+      if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
+      continue;
+    }
     trace_event(tr.n, 2);
     twait(tr, 2, &s.w_full[stage], phase);
     trace_event(tr.n, 3);
@@ -464,7 +500,7 @@ __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& 
     }
     __syncwarp();
     ++tr.n;
-    if (++stage == kStages) { stage = 0; phase ^= 1; }
+    if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
   }
 }
 
@@ -482,8 +518,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   float* s_w7r0 = reinterpret_cast<float*>(smem + kOffW7r0);
   float* s_w9 = reinterpret_cast<float*>(smem + kOffW9);
   float* s_misc = reinterpret_cast<float*>(smem + kOffMisc);   // [0]=b7[0], [1..3]=b9, [8..23]=c2f weights
-  float* s_part = reinterpret_cast<float*>(smem + kOffPart);   // [h][row][4]
-  const ChainSmem cs = chain_carve(smem);
+  float* s_part = reinterpret_cast<float*>(smem + kOffPart);   // [cq - 1][row][4]
+  const ChainSmem cs = chain_carve(smem, kOffRing, kStages);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -518,13 +554,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
   const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
 
-  if (warp == 0 || warp >= 2 + kEpiWarps) {
-    const int pidx = warp == 0 ? 0 : warp - (1 + kEpiWarps);
-    if (kPair) { if (pidx == 0) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false); }
-    else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1, pidx);   // whole warp, one elected lane issues
-  } else if (warp == 1) {
+  if (warp == 0) {
+    if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
+    else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1, 0);   // whole warp, one elected lane issues
+  } else if (warp == 1 || warp == 2 + kEpiWarps) {
+    const int issuer = warp == 1 ? 0 : 1;
     // ============================== MMA issuer ==============================
-    if (kPair && rank == 1) {
+    if (kPair && issuer != 0) {
+      // the second issuer warp has no role in a CTA pair
+    } else if (kPair && rank == 1) {
       pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, true);   // relay "my half landed" to the leader
     } else if (kPair) {
       const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
@@ -585,19 +623,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
             tc_fence_after();
             for (int nh = 0; nh < nh_cnt; ++nh)
               chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
-                                kbi == 0, p.passes, tr);
+                                kbi == 0, p.passes, nh_cnt == 1 ? issuer == 0 : nh == issuer, tr);
           }
-          if (elect_one()) umma_commit(&cs.d_full[buf]);            // accumulator of layer l complete
+          if (elect_one()) umma_commit(&cs.d_full[buf]);            // this warp's share of layer l's accumulator complete
           __syncwarp();
         }
       }
-      if (lane == 0) trace_end(tr, 1);
+      if (lane == 0 && issuer == 0) trace_end(tr, 1);
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // ============================== epilogue warps ==============================
     const int e = warp - 2;
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
-    const int h = e >> 2;             // which 32-column half of every 64-column block
+    const int cq = e >> 2;            // which 16-column quarter of every 64-column block
     const int row = q * 32 + lane;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t d_cnt[2] = {0, 0};
@@ -622,11 +660,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
 #pragma unroll
           for (int c = 0; c < 3; ++c) x[c] = add_rn(p.origins[ray * 3 + c], mul_rn(p.dirs[ray * 3 + c], tv));
         }
-        float vals[32];
-        if (h == 0) { vals[0] = x[0]; vals[1] = x[1]; vals[2] = x[2]; vals[3] = 0.f; }
-        const int p0 = h == 0 ? 0 : 14, np = h == 0 ? 14 : 16, v0 = h == 0 ? 4 : 0;
+        float vals[16];
+        if (cq == 0) { vals[0] = x[0]; vals[1] = x[1]; vals[2] = x[2]; vals[3] = 0.f; }
+        const int p0 = cq == 0 ? 0 : 8 * cq - 2, np = cq == 0 ? 6 : 8, v0 = cq == 0 ? 4 : 0;   // 6 + 8 + 8 + 8 pairs
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           if (i < np) {
             int pr = p0 + i;
             int c = pr / kL, j = pr - c * kL;
@@ -638,11 +676,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
             vals[v0 + 2 * i + 1] = mul_rn(cs_, w);
           }
         }
-        split_store32<kF16>(vals, row, h * 32, smem + kOffEnc, smem + kOffEnc + kChunkBytes,
-                            save ? p.img.at(T_ENC, tile, 0, 0) : nullptr, save ? p.img.at(T_ENC, tile, 0, 1) : nullptr);
+        Split16 sp;
+        split16<kF16>(vals, sp);
+        store16(sp, row, cq * kEpiCols, smem + kOffEnc, smem + kOffEnc + kChunkBytes);
         if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) chain_arrive<kPair>(&cs.a_ready[4], rank);
+        if (save) {
+          if (kF16) split16<false>(vals, sp);
+          store16_image(sp, row, cq * kEpiCols, p.img.at(T_ENC, tile, 0, 0), p.img.at(T_ENC, tile, 0, 1));
+        }
       }
 
       // ---------------- layers
@@ -653,20 +696,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
         tc_fence_after();
         const int nchunk = l == 8 ? 2 : 4;
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;   // density row (l == 6) or rgb rows (l == 8)
+        uint32_t mbits[2] = {0u, 0u};               // ReLU mask of this thread's 16 columns in each block
         for (int j = 0; j < nchunk; ++j) {
-          uint32_t v[32];
-          const int col0 = j * 64 + h * 32;
-          tmem_ld32(tmem_base + t_lane + (uint32_t)(buf * 256 + col0), v);
+          uint32_t v[16];
+          const int col0 = j * 64 + cq * kEpiCols;
+          tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0), v);
           tmem_ld_wait();
-          float f[32];
+          float f[16];
           if (l < 8) {
             const float* b = s_bias + l * 256 + col0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + b[i], 0.f);
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + b[i], 0.f);
           } else {
             const float* b = p.raybias + (size_t)ray * kHW + col0;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < 16; i += 4) {
               float4 bb = *reinterpret_cast<const float4*>(b + i);
               f[i] = fmaxf(__uint_as_float(v[i]) + bb.x, 0.f);
               f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + bb.y, 0.f);
@@ -676,53 +720,73 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
           }
           if (l == 6) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dot0 = fmaf(f[i], s_w7r0[col0 + i], dot0);
+            for (int i = 0; i < 16; ++i) dot0 = fmaf(f[i], s_w7r0[col0 + i], dot0);
           }
+          if (save) {
+            uint32_t m16 = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m16 |= (f[i] > 0.f ? 1u : 0u) << i;
+            mbits[j >> 1] |= m16 << (16 * (j & 1));
+          }
+          Split16 sp;
           if (l == 8) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16; ++i) {
               dot0 = fmaf(f[i], s_w9[col0 + i], dot0);
               dot1 = fmaf(f[i], s_w9[128 + col0 + i], dot1);
               dot2 = fmaf(f[i], s_w9[256 + col0 + i], dot2);
             }
-            if (save)   // hid image for the 128->3 head's weight gradient and its ReLU mask
-              split_store32<kF16>(f, row, h * 32, nullptr, nullptr, p.img.at(T_HID, tile, j, 0), p.img.at(T_HID, tile, j, 1));
+            if (save) {   // hid image for the 128->3 head's weight gradient and its ReLU mask
+              split16<false>(f, sp);
+              store16_image(sp, row, cq * kEpiCols, p.img.at(T_HID, tile, j, 0), p.img.at(T_HID, tile, j, 1));
+            }
           } else {
-            const int tsave = l == 7 ? T_FEAT : T_H0 + l;
-            split_store32<kF16>(f, row, h * 32, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes,
-                                save ? p.img.at(tsave, tile, j, 0) : nullptr, save ? p.img.at(tsave, tile, j, 1) : nullptr);
+            split16<kF16>(f, sp);
+            store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
             if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
+            if (save) {
+              const int tsave = l == 7 ? T_FEAT : T_H0 + l;
+              if (kF16) split16<false>(f, sp);
+              store16_image(sp, row, cq * kEpiCols, p.img.at(tsave, tile, j, 0), p.img.at(tsave, tile, j, 1));
+            }
           }
         }
         // accumulator drained: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
+        if (save) *p.img.mask_at(tile, l, row, cq) = make_uint2(mbits[0], mbits[1]);
 
         if (l == 6 || l == 8) {
-          // combine the two column halves of each row (warps q and q+4) through shared memory
-          float* pr = s_part + ((size_t)h * 128 + row) * 4;
-          pr[0] = dot0; pr[1] = dot1; pr[2] = dot2;
+          // combine the four column quarters of each row (warps q, q+4, q+8, q+12) through shared memory
+          if (cq != 0) {
+            float* pr = s_part + ((size_t)(cq - 1) * 128 + row) * 4;
+            pr[0] = dot0; pr[1] = dot1; pr[2] = dot2;
+          }
           named_bar_sync(1, kEpiWarps * 32);
-          if (h == 0 && valid) {
-            const float* o = s_part + ((size_t)128 + row) * 4;
+          if (cq == 0 && valid) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const float* o = s_part + ((size_t)k * 128 + row) * 4;
+              dot0 += o[0]; dot1 += o[1]; dot2 += o[2];
+            }
             if (l == 6) {
-              float raw = dot0 + o[0] + s_misc[0];
+              float raw = dot0 + s_misc[0];
               float z = p.noise ? add_rn(raw, p.noise[m]) : raw;
               p.sigma[m] = softplus_f(z);
             } else {
-              p.rgb[m * 3 + 0] = sigmoid_f(dot0 + o[0] + s_misc[1]);
-              p.rgb[m * 3 + 1] = sigmoid_f(dot1 + o[1] + s_misc[2]);
-              p.rgb[m * 3 + 2] = sigmoid_f(dot2 + o[2] + s_misc[3]);
+              p.rgb[m * 3 + 0] = sigmoid_f(dot0 + s_misc[1]);
+              p.rgb[m * 3 + 1] = sigmoid_f(dot1 + s_misc[2]);
+              p.rgb[m * 3 + 2] = sigmoid_f(dot2 + s_misc[3]);
             }
           }
           named_bar_sync(1, kEpiWarps * 32);
         }
       }
     }
-    if (lane == 0 && (e == 0 || e == 7)) trace_end(tr, e == 0 ? 2 : 3);
+    if (lane == 0 && (e == 0 || e == kEpiWarps - 1)) trace_end(tr, e == 0 ? 2 : 3);
   }
 
   // ---- teardown
@@ -737,11 +801,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
 // ------------------------------------------------------------------------------------------------
 // the fused input-gradient (dgrad) kernel: dL/dz chain from the colour head to layer 0
 // ------------------------------------------------------------------------------------------------
-// 32-bit mask of (hi half > 0) for columns [col0, col0+32) of one row of a saved bf16 image block
+// 16-bit mask of (hi half > 0) for columns [col0, col0+16) of one row of a saved bf16 image block
 __device__ __forceinline__ uint32_t load_relu_mask(const uint8_t* img_hi, int row, int col0) {
   uint32_t mask = 0;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     const uint4 v = *reinterpret_cast<const uint4*>(img_hi + sw128_offset(row, col0 + c * 8));
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -761,7 +825,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* s_w7r0 = reinterpret_cast<float*>(smem + kOffW7r0);
   float* s_w9 = reinterpret_cast<float*>(smem + kOffW9);
-  const ChainSmem cs = chain_carve(smem);
+  const ChainSmem cs = chain_carve(smem, kOffEnc, kBwdStages);   // ring = the encoder blocks + the forward ring
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < 256; i += kThreads) s_w7r0[i] = p.w7[i];
@@ -782,12 +846,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
   const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
   const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
 
-  if (warp == 0 || warp >= 2 + kEpiWarps) {
-    const int pidx = warp == 0 ? 0 : warp - (1 + kEpiWarps);
-    if (kPair) { if (pidx == 0) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false); }
-    else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false, pidx);
-  } else if (warp == 1) {
-    if (kPair && rank == 1) {
+  if (warp == 0) {
+    if (kPair) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false);
+    else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false, 0);
+  } else if (warp == 1 || warp == 2 + kEpiWarps) {
+    const int issuer = warp == 1 ? 0 : 1;
+    if (kPair && issuer != 0) {
+      // the second issuer warp has no role in a CTA pair
+    } else if (kPair && rank == 1) {
       pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, true);
     } else if (kPair) {
       const uint32_t idesc = make_idesc(256, 256, 1);
@@ -834,18 +900,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             const uint32_t a_hi = act_addr + kbi * kChunkBytes, a_lo = act_addr + (4 + kbi) * kChunkBytes;
             for (int nh = 0; nh < 2; ++nh)
               chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
-                                kbi == 0, 3, tr);
+                                kbi == 0, 3, nh == issuer, tr);
           }
           if (elect_one()) umma_commit(&cs.d_full[buf]);
           __syncwarp();
         }
       }
-      if (lane == 0) trace_end(tr, 1);
+      if (lane == 0 && issuer == 0) trace_end(tr, 1);
     }
+  } else if (warp == 2 + kEpiWarps + kIssuers - 1) {
+    // ============================== gradient-image store warp ==============================
+    // streams every finished [128 x 64] hi / lo block pair (already in the HBM image layout) out with bulk copies
+    uint8_t* act_hi = smem + kOffAct;
+    uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
+      const bool tile_ok = tile < p.num_tiles;
+      for (int step = 0; step <= kNumBwdLayers; ++step) {          // step 0 = head (blocks 0, 1), step bl + 1 = layer bl
+        const int nblk = step == 0 ? 2 : 4;
+        const int t_out = step == 0 ? T_GHID : (step == 1 ? T_G7F : t_g(8 - step));
+        for (int j = 0; j < nblk; ++j) {
+          const uint32_t n = j < 2 ? 9u * (uint32_t)it + (uint32_t)step : 8u * (uint32_t)it + (uint32_t)step - 1u;
+          mbar_wait(&cs.g_ready[j], n & 1);
+          if (elect_one()) {
+            if (tile_ok) {
+              bulk_s2g(p.img.at(t_out, tile, j, 0), act_hi + (size_t)j * kChunkBytes, kChunkBytes);
+              bulk_s2g(p.img.at(t_out, tile, j, 1), act_lo + (size_t)j * kChunkBytes, kChunkBytes);
+              bulk_commit_group();
+              bulk_wait_read_all();
+            }
+            mbar_arrive(&cs.s_free[j]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (elect_one()) bulk_wait_all();
+    __syncwarp();
   } else {
     const int e = warp - 2;
     const int q = warp & 3;
-    const int h = e >> 2;
+    const int cq = e >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t d_cnt[2] = {0, 0};
@@ -869,62 +964,75 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         gp1 = p.d_rgb[m * 3 + 1] * c1 * (1.f - c1);
         gp2 = p.d_rgb[m * 3 + 2] * c2 * (1.f - c2);
         g_raw = p.d_sigma[m] * (-expm1f(-p.sigma[m]));
-        if (h == 0) {
+        if (cq == 0) {
           p.g_raw[m] = g_raw;
           *reinterpret_cast<float4*>(p.g_pre + m * 4) = make_float4(gp0, gp1, gp2, 0.f);
         }
       }
+      // Shared-memory block j is both the next layer's A operand and the source of the gradient image's bulk store
+      // (store warp below); write number n of a block must wait for the store of write n - 1 to have read it.
+      //   blocks 0, 1: n = 9 * it + (head: 0 | layer bl: bl + 1);   blocks 2, 3: n = 8 * it + bl
+      const uint2 hid_mask = *p.img.mask_at(tile, 8, row, cq);
 #pragma unroll 1
       for (int j = 0; j < 2; ++j) {
-        const int col0 = j * 64 + h * 32;
-        const uint32_t mask = load_relu_mask(p.img.at(T_HID, tile, j, 0), row, h * 32);
-        float f[32];
+        const int col0 = j * 64 + cq * kEpiCols;
+        const uint32_t mask = (hid_mask.x >> (16 * j)) & 0xFFFFu;
+        float f[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           float g = fmaf(gp2, s_w9[256 + col0 + i], fmaf(gp1, s_w9[128 + col0 + i], gp0 * s_w9[col0 + i]));
           f[i] = ((mask >> i) & 1u) ? g : 0.f;
         }
-        split_store32<false>(f, row, h * 32, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes,
-                             tile_ok ? p.img.at(T_GHID, tile, j, 0) : nullptr, tile_ok ? p.img.at(T_GHID, tile, j, 1) : nullptr);
+        Split16 sp;
+        split16<false>(f, sp);
+        const uint32_t n = 9u * (uint32_t)it;
+        if (n > 0) mbar_wait(&cs.s_free[j], (n - 1) & 1);
+        store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
         if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
+        if (lane == 0) { chain_arrive<kPair>(&cs.a_ready[j], rank); mbar_arrive(&cs.g_ready[j]); }
       }
 
       // ---------------- backward layers
       for (int bl = 0; bl < kNumBwdLayers; ++bl) {
         const int buf = bl & 1;
         // ReLU mask of the forward activation this gradient flows into: feat (bl 0), h6 (bl 1), ... h0 (bl 7)
-        const int t_mask = bl == 0 ? T_FEAT : T_H0 + (7 - bl);
-        const int t_out = bl == 0 ? T_G7F : t_g(7 - bl);
-        uint32_t masks[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) masks[j] = load_relu_mask(p.img.at(t_mask, tile, j, 0), row, h * 32);
+        long long tt = trace_tic();
+        const uint2 mk = *p.img.mask_at(tile, bl == 0 ? 7 : 7 - bl, row, cq);
+        const uint32_t masks[2] = {mk.x, mk.y};
+        trace_toc(tr, 1, tt);
         twait(tr, 0, &cs.d_full[buf], d_cnt[buf] & 1);
         ++d_cnt[buf];
         tc_fence_after();
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-          uint32_t v[32];
-          const int col0 = j * 64 + h * 32;
-          tmem_ld32(tmem_base + t_lane + (uint32_t)(buf * 256 + col0), v);
+          uint32_t v[16];
+          const int col0 = j * 64 + cq * kEpiCols;
+          long long tt2 = trace_tic();
+          tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0), v);
           tmem_ld_wait();
-          float f[32];
-          const uint32_t mask = masks[j];
+          trace_toc(tr, 2, tt2);
+          float f[16];
+          const uint32_t mask = (masks[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             float g = __uint_as_float(v[i]);
             if (bl == 1) g = fmaf(g_raw, s_w7r0[col0 + i], g);   // density row joins the feature gradient
             f[i] = ((mask >> i) & 1u) ? g : 0.f;
           }
           const bool chain = bl != kNumBwdLayers - 1;   // G0 is only saved, nothing consumes it on-chip
-          split_store32<false>(f, row, h * 32, chain ? act_hi + (size_t)j * kChunkBytes : nullptr,
-                               chain ? act_lo + (size_t)j * kChunkBytes : nullptr,
-                               tile_ok ? p.img.at(t_out, tile, j, 0) : nullptr, tile_ok ? p.img.at(t_out, tile, j, 1) : nullptr);
-          if (chain) {
-            if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
+          Split16 sp;
+          split16<false>(f, sp);
+          const uint32_t n = j < 2 ? 9u * (uint32_t)it + (uint32_t)bl + 1u : 8u * (uint32_t)it + (uint32_t)bl;
+          long long tt3 = trace_tic();
+          if (n > 0) mbar_wait(&cs.s_free[j], (n - 1) & 1);
+          trace_toc(tr, 3, tt3);
+          store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
+          if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (chain) chain_arrive<kPair>(&cs.a_ready[j], rank);
+            mbar_arrive(&cs.g_ready[j]);
           }
         }
         tc_fence_before();
@@ -932,7 +1040,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
       }
     }
-    if (lane == 0 && (e == 0 || e == 7)) trace_end(tr, e == 0 ? 2 : 3);
+    if (lane == 0 && (e == 0 || e == kEpiWarps - 1)) trace_end(tr, e == 0 ? 2 : 3);
   }
   tc_fence_before();
   __syncthreads();
@@ -953,12 +1061,13 @@ struct WgradJob {
   int ldw, col0;         // row stride and first column
   int enc_cols;          // 1: N' side is the encoder block (internal column order -> reference columns)
   float* colsum;         // optional: colsum[f] += sum_rows G[row][f]  (the layer's bias gradient), else NULL
+  int producers;         // 1: warp 0 streams both operand sides; 2: warp 6 takes the activation side
 };
 constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 16 * 4096;   // (4 G blocks + 4 X blocks) x (hi, lo) x 32 rows x 128 B
 constexpr int kWgSmem = kWgStages * kWgStageBytes + 256;
 
-__global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const WgradJob* __restrict__ jobs, Images img) {
+__global__ void __launch_bounds__(224, 1) tc_mlp_wgrad_kernel(const WgradJob* __restrict__ jobs, Images img) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
@@ -984,38 +1093,48 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const WgradJob* __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int nq = (job.tile_end - job.tile_begin) * 4;    // quarter tiles (32 rows) to stream
   const uint32_t stage_tx = (uint32_t)(job.mblk + job.nblk) * 2u * 4096u;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int qi = 0; qi < nq; ++qi) {
-        const int tile = job.tile_begin + (qi >> 2), qr = qi & 3;
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], stage_tx);
+  if (warp == 0 || warp == 6) {
+    // two producer warps (uniform control flow, an elected lane issues): warp 0 streams the gradient blocks and posts
+    // the stage's byte count, warp 6 streams the activation blocks
+    const bool g_side = warp == 0;
+    const bool x_side = job.producers == 2 ? warp == 6 : warp == 0;
+    uint32_t stage = 0, phase = 0;
+    for (int qi = 0; (g_side || x_side) && qi < nq; ++qi) {
+      const int tile = job.tile_begin + (qi >> 2), qr = qi & 3;
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* st = smem + stage * kWgStageBytes;
         // stage layout: [G hi: mblk x 4 KB][G lo][X hi: nblk x 4 KB][X lo], 4 KB = rows [32 qr, 32 qr + 32) of a block
-        for (int part = 0; part < 2; ++part) {
-          for (int b = 0; b < job.mblk; ++b)
-            bulk_g2s(st + (part * 4 + b) * 4096, img.at(job.t_g, tile, b, part) + qr * 4096, 4096, &full[stage]);
-          for (int b = 0; b < job.nblk; ++b)
-            bulk_g2s(st + (8 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
+        if (g_side) {
+          mbar_arrive_expect_tx(&full[stage], stage_tx);
+          for (int part = 0; part < 2; ++part)
+            for (int b = 0; b < job.mblk; ++b)
+              bulk_g2s(st + (part * 4 + b) * 4096, img.at(job.t_g, tile, b, part) + qr * 4096, 4096, &full[stage]);
         }
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        if (x_side) {
+          for (int part = 0; part < 2; ++part)
+            for (int b = 0; b < job.nblk; ++b)
+              bulk_g2s(st + (8 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
+        }
       }
+      __syncwarp();
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, ncols, 1, 1, 1);
-      uint32_t stage = 0, phase = 0;
-      for (int qi = 0; qi < nq; ++qi) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + stage * kWgStageBytes);
+    const uint32_t idesc = make_idesc(128, ncols, 1, 1, 1);
+    uint32_t stage = 0, phase = 0;
+    for (int qi = 0; qi < nq; ++qi) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + stage * kWgStageBytes);
+      if (elect_one()) {
         for (int mh = 0; mh < mhalves; ++mh) {
           const uint32_t d_addr = tmem_base + (uint32_t)(mh * ncols);
+#pragma unroll
           for (int ks = 0; ks < 2; ++ks) {   // 32 rows = 2 x K16
             const uint64_t g_hi = make_smem_desc_mn(st + (0 + mh * 2) * 4096 + ks * 2048, 4096);
             const uint64_t g_lo = make_smem_desc_mn(st + (4 + mh * 2) * 4096 + ks * 2048, 4096);
@@ -1027,10 +1146,12 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const WgradJob* __
           }
         }
         umma_commit(&empty[stage]);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done);
+      __syncwarp();
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
   } else {
     // warps 2..5: while the MMA warp streams, reduce the gradient images over the rows straight from the shared
     // memory stages (bias gradient = column sums of G); at the end flush the accumulator with atomics on dW
@@ -1449,11 +1570,12 @@ static size_t images_bytes(int ntiles, int t_begin, int t_end) {
   for (int t = t_begin; t < t_end; ++t) total += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles;
   return total;
 }
-static size_t fwd_images_bytes(int ntiles) { return images_bytes(ntiles, 0, T_GHID); }
+static size_t fwd_images_bytes(int ntiles) { return images_bytes(ntiles, 0, T_GHID) + (size_t)ntiles * kMaskTileBytes; }
 static size_t bwd_images_bytes(int ntiles) { return images_bytes(ntiles, T_GHID, T_COUNT); }
 static void images_assign(Images& img, int ntiles, uint8_t* fwd_base, uint8_t* bwd_base) {
   size_t o = 0;
   for (int t = 0; t < T_GHID; ++t) { img.ptr[t] = fwd_base ? fwd_base + o : nullptr; o += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles; }
+  img.mask = fwd_base ? fwd_base + o : nullptr;
   o = 0;
   for (int t = T_GHID; t < T_COUNT; ++t) { img.ptr[t] = bwd_base ? bwd_base + o : nullptr; o += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles; }
 }
@@ -1528,13 +1650,13 @@ static void trace_dump(const char* what) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h, g_tc_trace, sizeof(h));
   const char* roles[4] = {"producer0 (w0 = ring slot free)", "mma issuer (w0 = acc free, w1 = A ready, w2 = weights landed)",
-                          "epilogue warp 0 (w0 = acc full)", "epilogue warp 7 (w0 = acc full)"};
+                          "epilogue warp 0 (w0 = acc full, dgrad: w1 = mask loads, w2 = tmem ld, w3 = fence+arrive)", "epilogue warp 15"};
   fprintf(stderr, "[tc trace] %s, mean over CTAs 0..147 (clocks)\n", what);
   for (int r = 0; r < 4; ++r) {
     double a[5] = {0, 0, 0, 0, 0};
     for (int b = 0; b < 148; ++b)
       for (int k = 0; k < 5; ++k) a[k] += (double)h[((size_t)b * 4 + r) * 8 + k] / 148.0;
-    fprintf(stderr, "  %-70s total %9.0f  w0 %9.0f  w1 %9.0f  w2 %9.0f\n", roles[r], a[4], a[0], a[1], a[2]);
+    fprintf(stderr, "  %-70s total %9.0f  w0 %9.0f  w1 %9.0f  w2 %9.0f  w3 %9.0f\n", roles[r], a[4], a[0], a[1], a[2], a[3]);
   }
   if (getenv("SPARF_TC_TRACE_EVENTS")) {
     static long long ev[512 * 8];
@@ -1785,6 +1907,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     // 3. weight gradients: job table = (layer, slab of row tiles), ~one CTA per SM
     WgradJob jobs[256];
     int nj = 0;
+    static const int wg_producers = getenv("SPARF_WG_PRODUCERS") ? atoi(getenv("SPARF_WG_PRODUCERS")) : 1;
     auto add_jobs = [&](int tg, int tx, int mblk, int nblk, float* dW, int ldw, int col0, int enc, int slabs, float* colsum) {
       slabs = std::max(1, std::min(slabs, ntiles));
       for (int s = 0; s < slabs; ++s) {
@@ -1792,7 +1915,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
         j.t_g = tg; j.t_x = tx; j.mblk = mblk; j.nblk = nblk;
         j.tile_begin = (int)((long long)ntiles * s / slabs);
         j.tile_end = (int)((long long)ntiles * (s + 1) / slabs);
-        j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum;
+        j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum; j.producers = wg_producers;
         jobs[nj++] = j;
       }
     };
@@ -1805,7 +1928,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 10, nullptr);             // skip part of layer 4
     add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 10, grad->trunk_b[0]);          // layer 0 (+ its bias)
     SPARF_CHECK_CUDA(cudaMemcpyAsync(c.jobs, jobs, sizeof(WgradJob) * nj, cudaMemcpyHostToDevice, st));
-    tc_mlp_wgrad_kernel<<<nj, 192, kWgSmem + 1024, st>>>(c.jobs, img);
+    tc_mlp_wgrad_kernel<<<nj, 224, kWgSmem + 1024, st>>>(c.jobs, img);
     SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
 
     // 4. CUDA-core leftovers: biases, density row, 128->3 head, view-direction columns
