@@ -56,13 +56,19 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
-    def start(self):
+    def start(self, wait_s=5.0):
+        """Launch `nvidia-smi -lms 50` and block until its first row arrives (it needs ~0.5 s to come up; the timed
+        region of a short run would otherwise be over before the first sample)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < wait_s:
+                time.sleep(0.02)
+            self.rows.clear()   # samples from here on fall inside the measured regions
         except OSError:
             self.proc = None
 
@@ -154,7 +160,29 @@ def run_ours(args):
             dist.all_reduce(flat)  # one NCCL all-reduce of [d theta] per step
         return loss
 
-    def timed(n_warm, n_steps, e2e):
+    def local_step(ray_idx_dev):   # everything of a step except the cross-rank exchange
+        flat.zero_()
+        out = net.render_image_at_specific_rays(opt, data, iter=0, ray_idx=ray_idx_dev, mode="train")
+        gt = image_flat[:, ray_idx_dev]
+        loss = ops.huber2(out.rgb, gt)
+        loss.backward()
+        return loss.detach()
+
+    graphed = None
+    if args.graph:
+        from sparf_b200.graphs import GraphedStep
+        static_idx = idx_host[0].to(dev)
+        c0 = L.sparf_launch_count()
+        graphed = GraphedStep(local_step, (static_idx,), warmup=3)
+        launches_per_graph = (L.sparf_launch_count() - c0) // 4   # 3 eager warm-ups + the capture
+
+    def graph_step(ray_idx_src):
+        loss = graphed(ray_idx_src)
+        if world > 1:
+            dist.all_reduce(flat)
+        return loss
+
+    def timed(n_warm, n_steps, e2e, use_graph=False):
         times = []
         for i in range(n_warm + n_steps):
             src = idx_host[(n_total if e2e else 0) + i]
@@ -167,8 +195,8 @@ def run_ours(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if e2e:  # host buffers in, host scalar out, inside the timed region
-                ray_idx_dev = src.to(dev, non_blocking=True)
-            loss = step(ray_idx_dev)
+                ray_idx_dev = src if use_graph else src.to(dev, non_blocking=True)
+            loss = graph_step(ray_idx_dev) if use_graph else step(ray_idx_dev)
             if e2e:
                 loss_host.copy_(loss.detach(), non_blocking=True)
             e1.record()
@@ -192,8 +220,13 @@ def run_ours(args):
     total_ms, times = timed(0, args.steps, False)
     ops.PROFILE_ON[0] = False
     launches = L.sparf_launch_count() - launches0
-    mlp_ms = ops.profile_total_ms()
-    e2e_ms, _ = timed(args.warmup, args.steps, True)
+    mlp_ms = ops.profile_total_ms()   # MLP kernel groups timed with CUDA events in the eager pass (same kernels)
+    eager_ms_per_step = total_ms / args.steps
+    if graphed is not None:           # the reported step: one CUDA-graph replay per step
+        timed(args.warmup, 0, False, use_graph=True)
+        total_ms, times = timed(0, args.steps, False, use_graph=True)
+        launches = launches_per_graph * args.steps
+    e2e_ms, _ = timed(args.warmup, args.steps, True, use_graph=graphed is not None)
     clocks = sampler.stop() if rank == 0 else None   # sampled over the device-timed AND the end-to-end region
     if rank != 0:
         if world > 1:
@@ -217,6 +250,8 @@ def run_ours(args):
                 dtype="f32 in/out; GEMMs: " + args.engine, data="synthetic",
                 config=dict(workload=WORKLOAD, rays_per_gpu=B_VIEWS * RAYS_PER_VIEW, global_rays=rays_per_step,
                             samples_per_ray=S_COARSE, l2_flush_between_steps=True,
+                            launch="one CUDA-graph replay per step" if graphed is not None else "eager",
+                            eager_ms_per_step=eager_ms_per_step,
                             timing="mean of per-step CUDA-event intervals, max over ranks",
                             parallelism="dp%d (ray sharding, one NCCL all-reduce of MLP grads per step)" % world),
                 clocks=clocks,
@@ -315,6 +350,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

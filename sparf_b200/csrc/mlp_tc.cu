@@ -360,7 +360,13 @@ __device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem, int ring_off, in
 // ncta = 1: stand-alone CTA;  ncta = 2: CTA pair -- the leader's a_ready / d_empty collect the epilogue warps of
 // BOTH CTAs, w_peer[s] tells the leader that the peer's half of weight stage s has landed
 __device__ __forceinline__ void chain_init_barriers(const ChainSmem& s, int ncta = 1) {
-  for (int i = 0; i < s.nstages; ++i) { mbar_init(&s.w_full[i], 1); mbar_init(&s.w_empty[i], 1); mbar_init(&s.w_peer[i], 1); }
+  // w_empty: stand-alone CTA = the owning issuer's MMA commit + the other issuer's "seen it" (every waiter of a phase
+  // must gate the slot's reuse, or the ring can lap a slow waiter and its parity wait aliases); pair = the leader's commit
+  for (int i = 0; i < s.nstages; ++i) {
+    mbar_init(&s.w_full[i], 1);
+    mbar_init(&s.w_empty[i], ncta == 1 ? kIssuers : 1);
+    mbar_init(&s.w_peer[i], 1);
+  }
   for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps * ncta);
   for (int i = 0; i < 4; ++i) { mbar_init(&s.g_ready[i], kEpiWarps); mbar_init(&s.s_free[i], 1); }
   // d_full: one commit per issuer warp (stand-alone) or the leader's multicast commit (pair)
@@ -476,11 +482,26 @@ __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& 
                                                   uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes,
                                                   bool mine, Trace& tr) {
   const uint32_t ring_addr = smem_u32(s.ring);
-  for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
-    if (!mine) {   // the other issuer warp's chunk: only step the ring position
-      if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
-      continue;
+  if (!mine) {
+    // The other issuer warp's chunks.  They are still waited for: a waiter that skipped a phase of w_full[stage] could
+    // later find itself two phases ahead of the barrier, and a parity wait cannot tell "two ahead" from "complete".
+    // One combined poll covers the (hi, lo) pair.
+    const uint32_t s0 = stage, p0 = phase;
+    if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
+    if (passes == 1) {
+      mbar_wait(&s.w_full[s0], p0);
+      if (elect_one()) mbar_arrive(&s.w_empty[s0]);
+      __syncwarp();
+      return;
     }
+    const uint32_t s1 = stage;
+    mbar_wait_two(&s.w_full[s0], p0, &s.w_full[s1], phase);
+    if (elect_one()) { mbar_arrive(&s.w_empty[s0]); mbar_arrive(&s.w_empty[s1]); }
+    __syncwarp();
+    if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
+    return;
+  }
+  for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
     trace_event(tr.n, 2);
     twait(tr, 2, &s.w_full[stage], phase);
     trace_event(tr.n, 3);
@@ -1063,11 +1084,13 @@ struct WgradJob {
   float* colsum;         // optional: colsum[f] += sum_rows G[row][f]  (the layer's bias gradient), else NULL
   int producers;         // 1: warp 0 streams both operand sides; 2: warp 6 takes the activation side
 };
+constexpr int kMaxWgradJobs = 160;
+struct WgradJobs { WgradJob j[kMaxWgradJobs]; };   // passed by value (kernel parameter): no host->device copy per step
 constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 16 * 4096;   // (4 G blocks + 4 X blocks) x (hi, lo) x 32 rows x 128 B
 constexpr int kWgSmem = kWgStages * kWgStageBytes + 256;
 
-__global__ void __launch_bounds__(224, 1) tc_mlp_wgrad_kernel(const WgradJob* __restrict__ jobs, Images img) {
+__global__ void __launch_bounds__(224, 1) tc_mlp_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const __grid_constant__ Images img) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
@@ -1075,7 +1098,7 @@ __global__ void __launch_bounds__(224, 1) tc_mlp_wgrad_kernel(const WgradJob* __
   uint64_t* empty = bars + kWgStages;
   uint64_t* done = bars + 2 * kWgStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
-  const WgradJob job = jobs[blockIdx.x];
+  const WgradJob& job = jobs.j[blockIdx.x];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ncols = job.nblk * 64;                       // N'
   const int mhalves = job.mblk / 2;                      // accumulators of 128 rows
@@ -1245,6 +1268,8 @@ struct ReduceJob {
   float* out_bias;
 };
 
+struct ReduceJobs { ReduceJob j[16]; };
+
 __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&x)[8]) {
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
@@ -1254,10 +1279,10 @@ __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&
   }
 }
 
-__global__ void __launch_bounds__(256) image_reduce_kernel(const ReduceJob* __restrict__ jobs, Images img, long long M,
+__global__ void __launch_bounds__(256) image_reduce_kernel(const __grid_constant__ ReduceJobs jobs, Images img, long long M,
                                                            int ntiles, int tiles_per_block) {
   __shared__ float red[8][32][25];
-  const ReduceJob job = jobs[blockIdx.y];
+  const ReduceJob& job = jobs.j[blockIdx.y];
   const int tid = threadIdx.x, c16 = tid & 31, rg = tid >> 5;
   const int fb = c16 >> 3, c = c16 & 7;
   const bool active = fb < job.nblk;
@@ -1905,7 +1930,8 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
 
     // 3. weight gradients: job table = (layer, slab of row tiles), ~one CTA per SM
-    WgradJob jobs[256];
+    WgradJobs jobs_tab;
+    WgradJob* jobs = jobs_tab.j;
     int nj = 0;
     static const int wg_producers = getenv("SPARF_WG_PRODUCERS") ? atoi(getenv("SPARF_WG_PRODUCERS")) : 1;
     auto add_jobs = [&](int tg, int tx, int mblk, int nblk, float* dW, int ldw, int col0, int enc, int slabs, float* colsum) {
@@ -1927,12 +1953,12 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 16, grad->trunk_b[l]);
     add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 10, nullptr);             // skip part of layer 4
     add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 10, grad->trunk_b[0]);          // layer 0 (+ its bias)
-    SPARF_CHECK_CUDA(cudaMemcpyAsync(c.jobs, jobs, sizeof(WgradJob) * nj, cudaMemcpyHostToDevice, st));
-    tc_mlp_wgrad_kernel<<<nj, 224, kWgSmem + 1024, st>>>(c.jobs, img);
+    tc_mlp_wgrad_kernel<<<nj, 224, kWgSmem + 1024, st>>>(jobs_tab, img);
     SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
 
     // 4. CUDA-core leftovers: biases, density row, 128->3 head, view-direction columns
-    ReduceJob rj[16];
+    ReduceJobs rj_tab;
+    ReduceJob* rj = rj_tab.j;
     int nrj = 0;
     auto add_red = [&](int t, int nblk, int nc, const float* g, int gs, float* out, int ldo, float* ob) {
       ReduceJob j; j.t = t; j.nblk = nblk; j.nc = nc; j.g = g; j.gs = gs; j.out = out; j.ldo = ldo; j.out_bias = ob;
@@ -1941,9 +1967,8 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     // (bias gradients = column sums of the gradient images are produced inside the weight-gradient kernel)
     add_red(T_H0 + 6, 4, 1, c.g_raw, 1, grad->trunk_w[7], kW, grad->trunk_b[7]);        // density row of trunk 7
     add_red(T_HID, 2, 3, c.g_pre, 4, grad->head_w[1], kHW, grad->head_b[1]);             // 128 -> 3 colour layer
-    SPARF_CHECK_CUDA(cudaMemcpyAsync(c.rjobs, rj, sizeof(ReduceJob) * nrj, cudaMemcpyHostToDevice, st));
     const int tpb = 4;
-    image_reduce_kernel<<<dim3(ceil_div(ntiles, tpb), nrj), 256, 0, st>>>(c.rjobs, img, Mc, ntiles, tpb);
+    image_reduce_kernel<<<dim3(ceil_div(ntiles, tpb), nrj), 256, 0, st>>>(rj_tab, img, Mc, ntiles, tpb);
     SPARF_CHECK_LAUNCH("image_reduce_kernel");
     ray_sum_ghid_kernel<<<nr, 128, 0, st>>>(img, nr, S, c.rayS);
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");

@@ -62,6 +62,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// both of two local barriers (each with its own parity); the two polls are in flight together
+__device__ __forceinline__ void mbar_wait_two(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "and.pred p, p, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 26)) {
+      printf("sparf tc: double mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- CTA pairs
 // (thread-block cluster of 2, tcgen05 cta_group::2: one MMA spans both SMs, each SM holds half of B)
 __device__ __forceinline__ uint32_t cluster_ctarank() {

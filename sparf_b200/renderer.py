@@ -141,7 +141,7 @@ class Graph(torch.nn.Module):
             ret = self.render_by_slices(opt, pose, intr=data_dict.intr, mode=mode, H=H, W=W, depth_range=depth_range,
                                         iter=iter) if opt.nerf.rand_rays else \
                 self.render(opt, pose, intr=data_dict.intr, mode=mode, H=H, W=W, depth_range=depth_range, iter=iter)
-        ret.idx_img_rendered = torch.arange(start=0, end=batch_size).to(self.device)
+        ret.idx_img_rendered = torch.arange(start=0, end=batch_size, device=self.device)
         return ret
 
     def render_image_at_specific_pose_and_rays(self, opt, data_dict, pose, intr, H, W, iter, pixels=None,
@@ -187,7 +187,7 @@ class Graph(torch.nn.Module):
                               depth_range=depth_range, iter=iter)
             ret.ray_idx = ray_idx
         ret.idx_img_rendered = torch.from_numpy(np.array(img_idx)).to(self.device) if img_idx is not None else \
-            torch.arange(start=0, end=batch_size).to(self.device)
+            torch.arange(start=0, end=batch_size, device=self.device)
         return ret
 
     # ---------------------------------------------------------------------------- core
