@@ -1074,6 +1074,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
 // ------------------------------------------------------------------------------------------------
 // weight-gradient kernel: dW[m'][n'] += sum_rows G[row][m'] * X[row][n'] over a slab of row tiles
 // ------------------------------------------------------------------------------------------------
+// 8 bf16 (hi, lo) pairs -> fp32
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&x)[8]) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    x[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
+  }
+}
+
 struct WgradJob {
   int t_g, t_x;          // image tensors: gradient (M' side) and activation (N' side)
   int mblk, nblk;        // 64-column blocks on each side (M' = 64 mblk in {128, 256}; N' = 64 nblk in {64, 256})
@@ -1181,38 +1191,40 @@ __global__ void __launch_bounds__(224, 1) tc_mlp_wgrad_kernel(const __grid_const
     const int q = warp & 3;
     const int rowl = q * 32 + lane;
     {
-      const int rt = tid - 64;                 // 0..127
-      const int nfeat = job.mblk * 64;
-      float cs0 = 0.f, cs1 = 0.f;
+      // reducer warp w owns gradient block w of every stage: lane = (row group rg, 16-byte chunk c); 8 features x 8 rows
+      // per thread and stage with conflict-free 16-byte loads (8 consecutive lanes read one swizzled 128-byte row)
+      const int blk = warp - 2, c = lane & 7, rg = lane >> 3;
+      const bool has = job.colsum && blk < job.mblk;
+      float cs[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cs[k] = 0.f;
       uint32_t stage = 0, phase = 0;
       for (int qi = 0; qi < nq; ++qi) {
         mbar_wait(&full[stage], phase);
-        if (job.colsum) {
-          const uint8_t* st = smem + stage * kWgStageBytes;
+        if (has) {
+          const uint8_t* bh = smem + stage * kWgStageBytes + blk * 4096;
+          const uint8_t* bl = bh + 4 * 4096;
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int f = rt + u * 128;
-            if (f < nfeat) {
-              const uint8_t* bh = st + (f >> 6) * 4096;
-              const uint8_t* bl = st + (4 + (f >> 6)) * 4096;
-              float a = 0.f;
-#pragma unroll 8
-              for (int r = 0; r < 32; ++r) {
-                const uint32_t off = sw128_offset(r, f & 63);
-                a += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(bh + off)) << 16) +
-                     __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(bl + off)) << 16);
-              }
-              if (u == 0) cs0 += a; else cs1 += a;
-            }
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t off = (uint32_t)(rg * 8 + i) * 128u + (uint32_t)((c ^ i) << 4);
+            float x[8];
+            unpack8(*reinterpret_cast<const uint4*>(bh + off), *reinterpret_cast<const uint4*>(bl + off), x);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cs[k] += x[k];
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
-      if (job.colsum) {
-        if (rt < nfeat) atomicAdd(job.colsum + rt, cs0);
-        if (rt + 128 < nfeat) atomicAdd(job.colsum + rt + 128, cs1);
+      if (has) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float v = cs[k];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (rg == 0) atomicAdd(job.colsum + blk * 64 + c * 8 + k, v);
+        }
       }
     }
     mbar_wait(done, 0);
@@ -1269,15 +1281,6 @@ struct ReduceJob {
 };
 
 struct ReduceJobs { ReduceJob j[16]; };
-
-__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&x)[8]) {
-  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    x[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
-    x[2 * i + 1] = __uint_as_float(hw[i] & 0xFFFF0000u) + __uint_as_float(lw[i] & 0xFFFF0000u);
-  }
-}
 
 __global__ void __launch_bounds__(256) image_reduce_kernel(const __grid_constant__ ReduceJobs jobs, Images img, long long M,
                                                            int ntiles, int tiles_per_block) {
@@ -1945,14 +1948,15 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
         jobs[nj++] = j;
       }
     };
-    // slabs sized so that every CTA streams about the same number of bytes (the kernel is HBM-bound):
-    // per row tile 256 KB (256x256 jobs), 192 KB (head), 160 KB (encoder columns) => 16 / 12 / 10 slabs, 144 CTAs
-    add_jobs(T_GHID, T_FEAT, 2, 4, grad->head_w[0], kW + kEv, 0, 0, 12, grad->head_b[0]);     // head 0, feature part
-    add_jobs(T_G7F, T_H0 + 6, 4, 4, grad->trunk_w[7] + kW, kW, 0, 0, 16, grad->trunk_b[7] + 1);  // trunk 7 rows 1..256
+    // One CTA per SM in a single wave.  A stage (32 rows of one tile) costs about the same ~2.4k clocks whatever its
+    // width (it is bound by the latency of the 3-deep HBM pipeline, profiles/r01_ncu_chain.md), so the slabs equalise
+    // the number of stages per CTA rather than bytes: 10 job types x ~14.8 slabs = 147 CTAs.
+    add_jobs(T_GHID, T_FEAT, 2, 4, grad->head_w[0], kW + kEv, 0, 0, 14, grad->head_b[0]);     // head 0, feature part
+    add_jobs(T_G7F, T_H0 + 6, 4, 4, grad->trunk_w[7] + kW, kW, 0, 0, 15, grad->trunk_b[7] + 1);  // trunk 7 rows 1..256
     for (int l = 6; l >= 1; --l)
-      add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 16, grad->trunk_b[l]);
-    add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 10, nullptr);             // skip part of layer 4
-    add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 10, grad->trunk_b[0]);          // layer 0 (+ its bias)
+      add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 15, grad->trunk_b[l]);
+    add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 14, nullptr);             // skip part of layer 4
+    add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 14, grad->trunk_b[0]);          // layer 0 (+ its bias)
     tc_mlp_wgrad_kernel<<<nj, 224, kWgSmem + 1024, st>>>(jobs_tab, img);
     SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
 
@@ -1972,7 +1976,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     SPARF_CHECK_LAUNCH("image_reduce_kernel");
     ray_sum_ghid_kernel<<<nr, 128, 0, st>>>(img, nr, S, c.rayS);
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
-    ray_head_wgrad_kernel<<<ceil_div(nr, 64), 128, 0, st>>>(nr, 64, c.rayS, c.denc, grad->head_w[0]);
+    ray_head_wgrad_kernel<<<ceil_div(nr, 8), 128, 0, st>>>(nr, 8, c.rayS, c.denc, grad->head_w[0]);
     SPARF_CHECK_LAUNCH("ray_head_wgrad_kernel");
 
     // 5. gradients w.r.t. the rays (camera-pose optimisation)
