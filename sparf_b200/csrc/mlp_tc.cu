@@ -1298,24 +1298,37 @@ __global__ void __launch_bounds__(256) image_reduce_kernel(const __grid_constant
   for (int tile = t0; tile < t1; ++tile) {
     const uint8_t* bh = img.at(job.t, tile, active ? fb : 0, 0);
     const uint8_t* bl = img.at(job.t, tile, active ? fb : 0, 1);
-    for (int row = rg; row < 128; row += 8) {
-      const long long m = (long long)tile * 128 + row;
-      if (m >= M) break;
-      if (!active) continue;
-      const uint32_t off = sw128_offset(row, c * 8);
-      float x[8];
-      unpack8(*reinterpret_cast<const uint4*>(bh + off), *reinterpret_cast<const uint4*>(bl + off), x);
-      if (nc == 0) {
+    if (!active) continue;
+#pragma unroll 1
+    for (int r0 = rg; r0 < 128; r0 += 32) {     // 4 rows per pass: 8 independent 16-byte loads in flight per thread
+      uint4 vh[4], vl[4];
+      float gv[4][3];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += x[i];
-      } else {
+      for (int u = 0; u < 4; ++u) {
+        const int row = r0 + 8 * u;
+        const long long m = (long long)tile * 128 + row;
+        const uint32_t off = sw128_offset(row, c * 8);
+        const bool ok = m < M;
+        vh[u] = ok ? __ldg(reinterpret_cast<const uint4*>(bh + off)) : make_uint4(0, 0, 0, 0);
+        vl[u] = ok ? __ldg(reinterpret_cast<const uint4*>(bl + off)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          if (k < nc) {
-            const float gv = job.g[m * job.gs + k];
+        for (int k = 0; k < 3; ++k) gv[u][k] = (ok && k < nc) ? __ldg(job.g + m * job.gs + k) : 0.f;
+      }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[k * 8 + i] = fmaf(gv, x[i], acc[k * 8 + i]);
-            if (c16 == 0) accb[k] += gv;
+      for (int u = 0; u < 4; ++u) {
+        float x[8];
+        unpack8(vh[u], vl[u], x);
+        if (nc == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += x[i];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (k < nc) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[k * 8 + i] = fmaf(gv[u][k], x[i], acc[k * 8 + i]);
+              if (c16 == 0) accb[k] += gv[u][k];
+            }
           }
         }
       }
