@@ -718,11 +718,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
         const int nchunk = l == 8 ? 2 : 4;
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;   // density row (l == 6) or rgb rows (l == 8)
         uint32_t mbits[2] = {0u, 0u};               // ReLU mask of this thread's 16 columns in each block
+        uint32_t vn[16];                            // accumulator columns of the NEXT block, loaded one block ahead
+        tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
         for (int j = 0; j < nchunk; ++j) {
           uint32_t v[16];
           const int col0 = j * 64 + cq * kEpiCols;
-          tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0), v);
           tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = vn[i];
+          if (j + 1 < nchunk) tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0 + 64), vn);
           float f[16];
           if (l < 8) {
             const float* b = s_bias + l * 256 + col0;
@@ -1025,13 +1029,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         twait(tr, 0, &cs.d_full[buf], d_cnt[buf] & 1);
         ++d_cnt[buf];
         tc_fence_after();
+        uint32_t vn[16];                            // accumulator columns of the NEXT block, loaded one block ahead
+        tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           uint32_t v[16];
           const int col0 = j * 64 + cq * kEpiCols;
           long long tt2 = trace_tic();
-          tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0), v);
           tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = vn[i];
+          if (j + 1 < 4) tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0 + 64), vn);
           trace_toc(tr, 2, tt2);
           float f[16];
           const uint32_t mask = (masks[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
@@ -1674,15 +1682,21 @@ static int weight_copies() {
   return v;
 }
 
-// CTA-pair (cta_group::2) variants of the chain kernels: correct and tested, but measured ~10% SLOWER than the
-// stand-alone-CTA kernels on this workload (profiles/r01_notes.md), so they are opt-in: SPARF_TC_PAIRS=1
-static bool use_cta_pairs() {
-  static int v = -1;
-  if (v < 0) {
+// CTA-pair (cta_group::2) variants of the chain kernels.  Measured on the bench shape (profiles/r01_notes.md): the
+// inference forward is ~11% faster as pairs (half the weight bytes and operand-fetch bandwidth per SM), the taped
+// forward and the dgrad chain are slower (every epilogue hand-off becomes a cluster-scope arrive on the leader).
+// Default: pairs for the inference forward only; SPARF_TC_PAIRS=0 / 1 forces them off / on everywhere.
+static int cta_pairs_mode() {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("SPARF_TC_PAIRS");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = e ? (e[0] == '1' ? 1 : 0) : -1;
   }
-  return v == 1;
+  return v;
+}
+static bool use_cta_pairs(bool inference) {
+  const int m = cta_pairs_mode();
+  return m < 0 ? inference : m == 1;
 }
 
 #ifdef SPARF_TC_TRACE
@@ -1764,7 +1778,7 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_encgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgSmem + 1024));
     attr_set = true;
   }
-  if (use_cta_pairs() && p.num_tiles >= 2) {
+  if (use_cta_pairs(!p.save) && p.num_tiles >= 2) {
     const int pairs = (p.num_tiles + 1) / 2;
     const int grid = 2 * std::min(pairs, num_sms() / 2);
     rc_launch = f16 ? launch_clustered(tc_mlp_fwd_kernel<true, true>, grid, kThreads, kSmemBytes + 1024, st, p)
@@ -1932,7 +1946,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     bp.g_raw = c.g_raw; bp.g_pre = c.g_pre;
     bp.w7 = mlp->trunk_w[7]; bp.w9 = mlp->head_w[1];
     bp.M = Mc; bp.num_tiles = ntiles; bp.img = img;
-    if (use_cta_pairs() && ntiles >= 2) {
+    if (use_cta_pairs(false) && ntiles >= 2) {
       const int grid = 2 * std::min((ntiles + 1) / 2, num_sms() / 2);
       cudaError_t le = launch_clustered(tc_mlp_dgrad_kernel<true>, grid, kThreads, kSmemBytes + 1024, st, bp);
       if (le != cudaSuccess) {
