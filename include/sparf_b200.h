@@ -178,6 +178,17 @@ int sparf_composite_backward(int32_t R, int32_t S, const float* sigma, const flo
 int sparf_huber2_fwd_bwd(int64_t n, const float* pred, const float* target, float scale, float* loss,
                          float* d_pred, sparf_stream_t stream);
 
+/* ---------------------------------------------------------------- parameter update
+ * One optimiser group over FLAT fp32 buffers of n elements: non-finite-gradient check (a bad gradient skips the
+ * update), clip_grad_norm_(max_norm; <= 0: none), torch.optim.Adam (betas, eps, no weight decay / amsgrad) with
+ * lr = lr0 * gamma^(k-1) [* min(1, k / warmup_steps) if warmup_steps > 0] at iteration k = step[1] + 1 and bias
+ * corrections of update t = step[0] + 1; then step[1] = k and, unless skipped, step[0] = t.  Replaces iter_based_trainer.py:128-147 (after_backward), nerf_trainer.py:181-204 (Adam +
+ * ExponentialLR) and joint_pose_nerf_trainer.py:513-549 (update_parameters).  `step` (two int64) and `scratch`
+ * (>= 4 doubles, zero before the first call) live in device memory: no host round trip, CUDA-graph capturable. */
+int sparf_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t* step,
+                    double* scratch, double lr0, double gamma, double warmup_steps, double beta1, double beta2,
+                    double eps, double max_norm, sparf_stream_t stream);
+
 /* ---------------------------------------------------------------- diagnostics
  * Minimal tcgen05 GEMM exercising every Blackwell primitive of the tensor-core engine (operand layout,
  * descriptors, bulk copy, TMEM): D[128,128] = bf16(A[128,K]) * bf16(B[128,K])^T, K in {64,...,256}.
