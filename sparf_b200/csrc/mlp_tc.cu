@@ -54,7 +54,6 @@ constexpr int kMaxStages = 6;
 constexpr int kChunkBytes = 16384;  // one [128 x 64] 16-bit operand block
 constexpr int kEpiWarps = 16;       // 4 TMEM lane quadrants x 4 column quarters of every 64-column block
 constexpr int kEpiCols = 16;        // columns per epilogue warp and block
-constexpr int kProducers = 1;                   // weight-producer warps (warp 0, then the warps after the epilogue warps)
 constexpr int kIssuers = 2;                     // MMA-issuing warps of a stand-alone CTA: warp 1 owns accumulator columns
                                                // 0..127 (N half 0), the warp after the epilogue warps owns N half 1.
                                                // One warp alone spends ~800 clk of dependent uniform-datapath work per
@@ -453,14 +452,15 @@ __device__ __forceinline__ void pair_issue_block(const ChainSmem& s, uint32_t& s
   }
 }
 
-// weight producers: producer `pidx` of `kProducers` (one thread each, in different warps) owns ring stage `pidx`
-// and streams every kProducers-th 16 KB chunk of the per-tile sequence of `nchunks` chunks
+// weight producer (warp 0, uniform control flow, an elected lane issues): streams the per-tile sequence of `nchunks`
+// 16 KB chunks through the ring.  (Three producer warps, one per stage, measured no faster: the ring is drained by
+// the MMA warps, not starved by the copies.)
 __device__ __forceinline__ void chain_producer(const ChainSmem& s, const uint8_t* packed, int my_tiles, int nchunks,
-                                               bool skip_lo, int pidx) {
+                                               bool skip_lo) {
   Trace tr; trace_begin(tr);
   const int n_eff = skip_lo ? nchunks / 2 : nchunks;
   const long long total = (long long)my_tiles * n_eff;
-  for (long long g = pidx; g < total; g += kProducers) {
+  for (long long g = 0; g < total; ++g) {
     const int c_eff = (int)(g % n_eff);
     const int c = skip_lo ? 2 * c_eff : c_eff;
     const uint32_t stage = (uint32_t)(g % s.nstages), phase = (uint32_t)((g / s.nstages) & 1);
@@ -473,7 +473,7 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const uint8_t
     }
     __syncwarp();
   }
-  if (pidx == 0 && (threadIdx.x & 31) == 0) trace_end(tr, 0);
+  if ((threadIdx.x & 31) == 0) trace_end(tr, 0);
 }
 
 // one (K block, N half): waits for its weight chunks and issues the MMAs of all passes.  Called by the WHOLE issuer
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
 
   if (warp == 0) {
     if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
-    else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1, 0);   // whole warp, one elected lane issues
+    else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1);
   } else if (warp == 1 || warp == 2 + kEpiWarps) {
     const int issuer = warp == 1 ? 0 : 1;
     // ============================== MMA issuer ==============================
@@ -826,24 +826,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
 // ------------------------------------------------------------------------------------------------
 // the fused input-gradient (dgrad) kernel: dL/dz chain from the colour head to layer 0
 // ------------------------------------------------------------------------------------------------
-// 16-bit mask of (hi half > 0) for columns [col0, col0+16) of one row of a saved bf16 image block
-__device__ __forceinline__ uint32_t load_relu_mask(const uint8_t* img_hi, int row, int col0) {
-  uint32_t mask = 0;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const uint4 v = *reinterpret_cast<const uint4*>(img_hi + sw128_offset(row, col0 + c * 8));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-      uint32_t lo16 = w[i] & 0xFFFFu, hi16 = w[i] >> 16;
-      mask |= (uint32_t)((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0) << (c * 8 + 2 * i);
-      mask |= (uint32_t)((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0) << (c * 8 + 2 * i + 1);
-    }
-  }
-  return mask;
-}
-
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -873,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
 
   if (warp == 0) {
     if (kPair) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false);
-    else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false, 0);
+    else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false);
   } else if (warp == 1 || warp == 2 + kEpiWarps) {
     const int issuer = warp == 1 ? 0 : 1;
     if (kPair && issuer != 0) {
@@ -1100,7 +1082,6 @@ struct WgradJob {
   int ldw, col0;         // row stride and first column
   int enc_cols;          // 1: N' side is the encoder block (internal column order -> reference columns)
   float* colsum;         // optional: colsum[f] += sum_rows G[row][f]  (the layer's bias gradient), else NULL
-  int producers;         // 1: warp 0 streams both operand sides; 2: warp 6 takes the activation side
 };
 constexpr int kMaxWgradJobs = 160;
 struct WgradJobs { WgradJob j[kMaxWgradJobs]; };   // passed by value (kernel parameter): no host->device copy per step
@@ -1108,7 +1089,7 @@ constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 16 * 4096;   // (4 G blocks + 4 X blocks) x (hi, lo) x 32 rows x 128 B
 constexpr int kWgSmem = kWgStages * kWgStageBytes + 256;
 
-__global__ void __launch_bounds__(224, 1) tc_mlp_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const __grid_constant__ Images img) {
+__global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_constant__ WgradJobs jobs, const __grid_constant__ Images img) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
@@ -1138,28 +1119,22 @@ __global__ void __launch_bounds__(224, 1) tc_mlp_wgrad_kernel(const __grid_const
   const int nq = (job.tile_end - job.tile_begin) * 4;    // quarter tiles (32 rows) to stream
   const uint32_t stage_tx = (uint32_t)(job.mblk + job.nblk) * 2u * 4096u;
 
-  if (warp == 0 || warp == 6) {
-    // two producer warps (uniform control flow, an elected lane issues): warp 0 streams the gradient blocks and posts
-    // the stage's byte count, warp 6 streams the activation blocks
-    const bool g_side = warp == 0;
-    const bool x_side = job.producers == 2 ? warp == 6 : warp == 0;
+  if (warp == 0) {
+    // producer warp (uniform control flow, an elected lane issues).  A second producer warp for the activation side
+    // measured no faster: the kernel is bound by HBM latency / bandwidth, not by the issue rate of the copies.
     uint32_t stage = 0, phase = 0;
-    for (int qi = 0; (g_side || x_side) && qi < nq; ++qi) {
+    for (int qi = 0; qi < nq; ++qi) {
       const int tile = job.tile_begin + (qi >> 2), qr = qi & 3;
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* st = smem + stage * kWgStageBytes;
         // stage layout: [G hi: mblk x 4 KB][G lo][X hi: nblk x 4 KB][X lo], 4 KB = rows [32 qr, 32 qr + 32) of a block
-        if (g_side) {
-          mbar_arrive_expect_tx(&full[stage], stage_tx);
-          for (int part = 0; part < 2; ++part)
-            for (int b = 0; b < job.mblk; ++b)
-              bulk_g2s(st + (part * 4 + b) * 4096, img.at(job.t_g, tile, b, part) + qr * 4096, 4096, &full[stage]);
-        }
-        if (x_side) {
-          for (int part = 0; part < 2; ++part)
-            for (int b = 0; b < job.nblk; ++b)
-              bulk_g2s(st + (8 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
+        mbar_arrive_expect_tx(&full[stage], stage_tx);
+        for (int part = 0; part < 2; ++part) {
+          for (int b = 0; b < job.mblk; ++b)
+            bulk_g2s(st + (part * 4 + b) * 4096, img.at(job.t_g, tile, b, part) + qr * 4096, 4096, &full[stage]);
+          for (int b = 0; b < job.nblk; ++b)
+            bulk_g2s(st + (8 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
         }
       }
       __syncwarp();
@@ -1963,7 +1938,6 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     WgradJobs jobs_tab;
     WgradJob* jobs = jobs_tab.j;
     int nj = 0;
-    static const int wg_producers = getenv("SPARF_WG_PRODUCERS") ? atoi(getenv("SPARF_WG_PRODUCERS")) : 1;
     auto add_jobs = [&](int tg, int tx, int mblk, int nblk, float* dW, int ldw, int col0, int enc, int slabs, float* colsum) {
       slabs = std::max(1, std::min(slabs, ntiles));
       for (int s = 0; s < slabs; ++s) {
@@ -1971,7 +1945,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
         j.t_g = tg; j.t_x = tx; j.mblk = mblk; j.nblk = nblk;
         j.tile_begin = (int)((long long)ntiles * s / slabs);
         j.tile_end = (int)((long long)ntiles * (s + 1) / slabs);
-        j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum; j.producers = wg_producers;
+        j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum;
         jobs[nj++] = j;
       }
     };
@@ -1984,7 +1958,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 15, grad->trunk_b[l]);
     add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 14, nullptr);             // skip part of layer 4
     add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 14, grad->trunk_b[0]);          // layer 0 (+ its bias)
-    tc_mlp_wgrad_kernel<<<nj, 224, kWgSmem + 1024, st>>>(jobs_tab, img);
+    tc_mlp_wgrad_kernel<<<nj, 192, kWgSmem + 1024, st>>>(jobs_tab, img);
     SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
 
     // 4. CUDA-core leftovers: biases, density row, 128->3 head, view-direction columns
