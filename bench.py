@@ -242,7 +242,11 @@ def run_ours(args):
                     achieved=achieved, peak=peaks["bf16_tflops"], unit="TFLOP/s",
                     frac=(achieved / peaks["bf16_tflops"]) if achieved else None, peak_source=peaks["source"] + ", burst bf16",
                     frac_of_sustained=(achieved / peaks["bf16_tflops_sustained"]) if achieved and peaks["bf16_tflops_sustained"] else None,
-                    flop_per_launch_group=flop_step_gpu, ms_per_launch_group=mlp_ms_per_step, traffic=None,
+                    flop_per_launch_group=flop_step_gpu, ms_per_launch_group=mlp_ms_per_step,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the three dominant kernels of the group (taped
+                    # forward 1.217 GB, dgrad 1.142 GB, wgrad 2.393 GB), one ncu --set full capture at this shape
+                    traffic=4.752e9 if args.engine in ("auto", "tc_3x") else None,
+                    traffic_source="profiles/r01_ncu_chain.md (ncu --set full, per step)",
                     engine=args.engine)
     cpu = cpu_baseline(sample_steps=2)
     line = dict(metric="rays/sec (fwd+bwd, 128 samples/ray)", value=value, unit="rays/s", n_gpus=world, steps=args.steps,
