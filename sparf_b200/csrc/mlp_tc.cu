@@ -49,7 +49,8 @@ constexpr int kNumLayers = 9;    // forward tensor-core layers: trunk 0..7 + hea
 constexpr int kNumBwdLayers = 8; // backward tensor-core layers
 constexpr int kTileM = 128;
 constexpr int kStages = 3;         // weight-ring stages of the forward kernel
-constexpr int kBwdStages = 5;      // ... of the dgrad kernel, whose ring also takes the two encoder blocks it does not use
+constexpr int kBwdStages = 6;      // ... of the dgrad kernel: its ring takes everything between the activations and the
+                                   // barriers (encoder blocks, forward ring, bias / small-weight tables it does not use)
 constexpr int kMaxStages = 6;
 constexpr int kChunkBytes = 16384;  // one [128 x 64] 16-bit operand block
 constexpr int kEpiWarps = 16;       // 4 TMEM lane quadrants x 4 column quarters of every 64-column block
@@ -83,6 +84,8 @@ constexpr int kOffPart = kOffMisc + 32 * 4;              // 3 x 128 x 4 floats: 
 constexpr int kOffBar = kOffPart + 3 * 128 * 4 * 4;      // mbarriers
 constexpr int kNumBars = 3 * kMaxStages + 5 + 4 + 8;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
+constexpr int kOffBarBwd = kOffEnc + kBwdStages * kChunkBytes;   // dgrad: barriers right after its ring
+static_assert(kOffBarBwd + kNumBars * 8 + 16 <= kSmemBytes, "dgrad shared-memory map exceeds the launch size");
 static_assert(kSmemBytes + 1024 <= 232448, "shared memory budget exceeded");
 
 // ---- saved operand images (HBM): tensor t, tile, 64-column block, part (hi | lo): 16 KB each
@@ -201,7 +204,8 @@ __global__ void pack_weights_bwd_kernel(PackParams pp) {
     base += n;
   }
   int rel = chunk - base;
-  int part = rel & 1, nh = (rel >> 1) & 1, kbi = rel >> 2;
+  int nh = rel & 1, part = (rel >> 1) & 1, kbi = rel >> 2;   // (K block, part, N half): the two N halves of a part are
+                                                             // adjacent, so one N = 256 MMA can span them
   // source layer and its row offset / leading dimension
   const int l = bl == 0 ? 8 : (bl == 1 ? 7 : 8 - bl);
   const int ldw = l == 4 ? 319 : (l == 8 ? 283 : 256);
@@ -338,12 +342,12 @@ struct ChainSmem {
   uint32_t* tmem_slot;
 };
 
-__device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem, int ring_off, int nstages) {
+__device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem, int ring_off, int nstages, int bar_off = kOffBar) {
   ChainSmem s;
   s.base = smem;
   s.ring = smem + ring_off;
   s.nstages = nstages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + bar_off);
   s.w_full = bars;
   s.w_empty = bars + kMaxStages;
   s.a_ready = bars + 2 * kMaxStages;
@@ -358,18 +362,18 @@ __device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem, int ring_off, in
 
 // ncta = 1: stand-alone CTA;  ncta = 2: CTA pair -- the leader's a_ready / d_empty collect the epilogue warps of
 // BOTH CTAs, w_peer[s] tells the leader that the peer's half of weight stage s has landed
-__device__ __forceinline__ void chain_init_barriers(const ChainSmem& s, int ncta = 1) {
+__device__ __forceinline__ void chain_init_barriers(const ChainSmem& s, int ncta = 1, int n_issuers = kIssuers) {
   // w_empty: stand-alone CTA = the owning issuer's MMA commit + the other issuer's "seen it" (every waiter of a phase
   // must gate the slot's reuse, or the ring can lap a slow waiter and its parity wait aliases); pair = the leader's commit
   for (int i = 0; i < s.nstages; ++i) {
     mbar_init(&s.w_full[i], 1);
-    mbar_init(&s.w_empty[i], ncta == 1 ? kIssuers : 1);
+    mbar_init(&s.w_empty[i], ncta == 1 ? n_issuers : 1);
     mbar_init(&s.w_peer[i], 1);
   }
   for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps * ncta);
   for (int i = 0; i < 4; ++i) { mbar_init(&s.g_ready[i], kEpiWarps); mbar_init(&s.s_free[i], 1); }
   // d_full: one commit per issuer warp (stand-alone) or the leader's multicast commit (pair)
-  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], ncta == 1 ? kIssuers : 1); mbar_init(&s.d_empty[i], kEpiWarps * ncta); }
+  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], ncta == 1 ? n_issuers : 1); mbar_init(&s.d_empty[i], kEpiWarps * ncta); }
   fence_barrier_init();
 }
 
@@ -382,7 +386,7 @@ __device__ __forceinline__ void chain_arrive(uint64_t* bar, uint32_t rank) {
 
 // ---- CTA-pair variants of the producer / issuer.  Weight stream of CTA `rank`: the chunks of its N half
 // (nh = rank); the 128-wide head layer splits its single chunk into two 64-row halves.
-//   fwd chunk index = base(l) + (kbi * nh_cnt + nh) * 2 + part ;  bwd = base(bl) + (kbi * 2 + nh) * 2 + part
+//   fwd chunk index = base(l) + (kbi * nh_cnt + nh) * 2 + part ;  bwd = base(bl) + (kbi * 2 + part) * 2 + nh
 __device__ __forceinline__ int fwd_chunk_base(int l) {
   int b = 0;
   for (int i = 0; i < l; ++i) b += layer_nkb(i) * layer_nh(i) * 2;
@@ -412,7 +416,8 @@ __device__ __forceinline__ void pair_weight_loop(const ChainSmem& s, const uint8
             mbar_wait(&s.w_full[stage], phase);
             if (elect_one()) mbar_arrive_cluster(map_to_cta(&s.w_peer[stage], 0));
           } else {
-            const int chunk = half ? base + kbi * 2 + part : base + (kbi * 2 + (int)rank) * 2 + part;
+            const int chunk = half ? base + kbi * 2 + part
+                                   : (kBwd ? base + (kbi * 2 + part) * 2 + (int)rank : base + (kbi * 2 + (int)rank) * 2 + part);
             const uint32_t bytes = half ? kChunkBytes / 2 : kChunkBytes;
             const uint8_t* src = packed + (size_t)chunk * kChunkBytes + (half ? rank * (kChunkBytes / 2) : 0);
             mbar_wait(&s.w_empty[stage], phase ^ 1);
@@ -823,6 +828,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   }
 }
 
+// N = 256 variant for rings whose chunk order is (K block, part, N half) and whose stage count is even: the two N
+// halves of a part sit in adjacent stages, i.e. form one [256 x 64] K-major operand, and ONE M128 x N256 MMA covers
+// them.  Half the instructions and barrier round trips per unit of tensor work (one issuer warp suffices) and
+// 96 instead of 128 B/clk of shared-memory operand fetch.
+__device__ __forceinline__ void chain_issue_pair256(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
+                                                    uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, Trace& tr) {
+  const uint32_t ring_addr = smem_u32(s.ring);
+  for (int part = 0; part < 2; ++part) {
+    long long t0 = trace_tic();
+    mbar_wait_two(&s.w_full[stage], phase, &s.w_full[stage + 1], phase);
+    trace_toc(tr, 2, t0);
+    tc_fence_after();
+    const uint32_t b_addr = ring_addr + stage * kChunkBytes;
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t db = make_smem_desc(b_addr + ks * 32);
+        const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
+        umma_ss(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
+        if (part == 0) umma_ss(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+      }
+      umma_commit(&s.w_empty[stage]);
+      umma_commit(&s.w_empty[stage + 1]);
+    }
+    __syncwarp();
+    stage += 2;
+    if (stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused input-gradient (dgrad) kernel: dL/dz chain from the colour head to layer 0
 // ------------------------------------------------------------------------------------------------
@@ -830,15 +865,15 @@ template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* s_w7r0 = reinterpret_cast<float*>(smem + kOffW7r0);
-  float* s_w9 = reinterpret_cast<float*>(smem + kOffW9);
-  const ChainSmem cs = chain_carve(smem, kOffEnc, kBwdStages);   // ring = the encoder blocks + the forward ring
+  // shared-memory map of this kernel: activations (8 blocks) | 6-stage weight ring | barriers.  The density row and the
+  // 128 -> 3 colour weights (2.5 KB, read by every thread) come from global memory through L1.
+  const float* __restrict__ s_w7r0 = p.w7;
+  const float* __restrict__ s_w9 = p.w9;
+  const ChainSmem cs = chain_carve(smem, kOffEnc, kBwdStages, kOffBarBwd);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < 256; i += kThreads) s_w7r0[i] = p.w7[i];
-  for (int i = tid; i < 3 * 128; i += kThreads) s_w9[i] = p.w9[i];
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  if (tid == 32) chain_init_barriers(cs, kPair ? 2 : 1);
+  if (tid == 32) chain_init_barriers(cs, kPair ? 2 : 1, 1);   // stand-alone: ONE issuer warp (N = 256 MMAs)
   if (kPair) cluster_sync_all();
   if (warp == 1) {
     if (kPair) { tmem_alloc2(cs.tmem_slot, 512); tmem_relinquish2(); }
@@ -886,8 +921,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           __syncwarp();
         }
       }
-    } else if (!kPair) {
-      const uint32_t idesc = make_idesc(128, 128, 1);
+    } else if (!kPair && issuer == 0) {
+      const uint32_t idesc = make_idesc(128, 256, 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct);
       uint32_t stage = 0, phase = 0;
       uint32_t a_cnt[4] = {0, 0, 0, 0};
@@ -905,15 +940,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             ++a_cnt[kbi];
             tc_fence_after();
             const uint32_t a_hi = act_addr + kbi * kChunkBytes, a_lo = act_addr + (4 + kbi) * kChunkBytes;
-            for (int nh = 0; nh < 2; ++nh)
-              chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
-                                kbi == 0, 3, nh == issuer, tr);
+            chain_issue_pair256(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, tr);
           }
           if (elect_one()) umma_commit(&cs.d_full[buf]);
           __syncwarp();
         }
       }
-      if (lane == 0 && issuer == 0) trace_end(tr, 1);
+      if (lane == 0) trace_end(tr, 1);
     }
   } else if (warp == 2 + kEpiWarps + kIssuers - 1) {
     // ============================== gradient-image store warp ==============================
