@@ -178,6 +178,13 @@ int sparf_composite_backward(int32_t R, int32_t S, const float* sigma, const flo
 int sparf_huber2_fwd_bwd(int64_t n, const float* pred, const float* target, float scale, float* loss,
                          float* d_pred, sparf_stream_t stream);
 
+/* mip-NeRF-360 distortion regulariser of the renderer's (t, weights) [R,S] (regularization_losses.py:20-48 as called
+ * from base_losses.py:166-172; default off in the reference's configs): loss += scale * mean over rays; d_w [R,S] and,
+ * if not NULL, d_t [R,S] are WRITTEN with scale * dLoss/d.  O(S) per ray (prefix sums over the monotone mid-points)
+ * instead of the reference's [S-1, S-1] matrix. */
+int sparf_distortion_fwd_bwd(int32_t R, int32_t S, const float* t, const float* w, float scale, float* loss,
+                             float* d_w, float* d_t, sparf_stream_t stream);
+
 /* ---------------------------------------------------------------- parameter update
  * One optimiser group over FLAT fp32 buffers of n elements: non-finite-gradient check (a bad gradient skips the
  * update), clip_grad_norm_(max_norm; <= 0: none), torch.optim.Adam (betas, eps, no weight decay / amsgrad) with

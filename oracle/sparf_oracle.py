@@ -314,3 +314,42 @@ def photometric_loss(out: Dict[str, Tensor], image: Tensor, ray_idx: Tensor) -> 
     if "rgb_fine" in out:
         loss = loss + huber2(out["rgb_fine"].reshape(gt.shape), gt)
     return loss
+
+
+# ----------------------------------------------------------------------------------------------
+# default-off regularisers                 (source/training/core/regularization_losses.py)
+# ----------------------------------------------------------------------------------------------
+def distortion_loss(t: Tensor, w: Tensor) -> Tensor:
+    """mip-NeRF-360 distortion loss, literal O(S^2) form.   regularization_losses.py:20-48 (normalize=False).
+    t, w: [..., S, 1] (the renderer's `t` and `weights`)."""
+    w, t = w[..., 0], t[..., 0]
+    ut = (t[..., 1:] + t[..., :-1]) / 2
+    w = w[..., 1:]
+    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
+    inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
+    intra = torch.sum(w ** 2 * torch.diff(t), dim=-1) / 3
+    return (inter + intra).mean()
+
+
+def depth_patch_loss(depths: Tensor, patch_size: int, charbonnier_padding: float = 0.001) -> Tensor:
+    """Charbonnier smoothness over depth patches.   regularization_losses.py:51-66."""
+    B = depths.shape[0]
+    d = depths.reshape(B, -1, patch_size ** 2)
+    resid_sq = (d[..., None] - d[..., None, :]) ** 2
+    return torch.sqrt(resid_sq + charbonnier_padding ** 2).mean()
+
+
+def regularization_losses(out: Dict[str, Tensor], distortion: bool, depth_patch: bool, patch_size: int = 2) -> Dict[str, Tensor]:
+    """base_losses.py:162-194: strengths 2e-3 (distortion) and 2e-2 (depth patch), coarse + fine summed."""
+    loss = {}
+    if distortion:
+        v = 2e-3 * distortion_loss(out["t"], out["weights"])
+        if "weights_fine" in out:
+            v = v + 2e-3 * distortion_loss(out["t_fine"], out["weights_fine"])
+        loss["distortion"] = v
+    if depth_patch:
+        v = 2e-2 * depth_patch_loss(out["depth"], patch_size)
+        if "depth_fine" in out:
+            v = v + 2e-2 * depth_patch_loss(out["depth_fine"], patch_size)
+        loss["depth_patch"] = v
+    return loss

@@ -125,3 +125,94 @@ extern "C" int sparf_adam_step(int64_t n, float* param, float* grad, float* exp_
   SPARF_CHECK_LAUNCH("adam_kernel");
   return SPARF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// mip-NeRF-360 distortion regulariser (source/training/core/regularization_losses.py:20-48; called with the
+// renderer's `t` and `weights`, base_losses.py:166-172).  The reference builds the [S-1, S-1] matrix |u_i - u_j| per
+// ray; along a ray the mid-points u are monotone, so the pair sum collapses to prefix sums:
+//   sum_ij a_i a_j |u_i - u_j| = 2 sum_i a_i (u_i A_i - M_i),  A_i = sum_{j<i} a_j,  M_i = sum_{j<i} a_j u_j
+// with a_i = w_{i+1}, u_i = (t_{i+1} + t_i) / 2, i = 0..S-2; plus sum_i a_i^2 (t_{i+1} - t_i) / 3.
+// One warp per ray, shuffle scans (like compositing).  loss += scale * mean over rays; d_w, d_t are written.
+// ------------------------------------------------------------------------------------------------
+namespace sparf {
+namespace {
+
+__device__ __forceinline__ float warp_excl_scan(float v, int lane, float& total) {
+  float x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  total = __shfl_sync(0xffffffffu, x, 31);
+  float e = __shfl_up_sync(0xffffffffu, x, 1);
+  return lane == 0 ? 0.f : e;
+}
+
+__global__ void __launch_bounds__(128) distortion_kernel(int R, int S, const float* __restrict__ t, const float* __restrict__ w,
+                                                         float scale, float* __restrict__ loss, float* __restrict__ d_w,
+                                                         float* __restrict__ d_t) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float* tr = t + (size_t)r * S;
+  const float* wr = w + (size_t)r * S;
+  const int n = S - 1;
+  // orientation: inverse-depth samples decrease along the ray; the pair term only needs monotone mid-points
+  const float sgn = tr[S - 1] >= tr[0] ? 1.f : -1.f;
+  // pass 1: totals (for the suffix sums) and the loss
+  float A_tot = 0.f, M_tot = 0.f;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const float a = i < n ? wr[i + 1] : 0.f;
+    const float u = i < n ? sgn * 0.5f * (tr[i + 1] + tr[i]) : 0.f;
+    float sa = a, sm = a * u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sm += __shfl_xor_sync(0xffffffffu, sm, o); }
+    A_tot += sa; M_tot += sm;
+  }
+  float A_run = 0.f, M_run = 0.f, acc = 0.f;
+  const float gs = scale / (float)R;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const bool ok = i < n;
+    const float a = ok ? wr[i + 1] : 0.f;
+    const float t0 = ok ? tr[i] : 0.f, t1 = ok ? tr[i + 1] : 0.f;
+    const float u = sgn * 0.5f * (t1 + t0), dt = t1 - t0;
+    float ta, tm;
+    const float A = A_run + warp_excl_scan(a, lane, ta);
+    const float M = M_run + warp_excl_scan(a * u, lane, tm);
+    A_run += ta; M_run += tm;
+    if (ok) {
+      const float A_gt = A_tot - A - a, M_gt = M_tot - M - a * u;          // sums over j > i
+      acc += 2.f * a * (u * A - M) + a * a * dt * (1.f / 3.f);
+      // d/da_i = 2 sum_j a_j |u_i - u_j| + 2 a_i dt_i / 3
+      d_w[(size_t)r * S + i + 1] = gs * (2.f * ((u * A - M) + (M_gt - u * A_gt)) + 2.f * a * dt * (1.f / 3.f));
+      if (d_t) {
+        const float du = gs * sgn * 2.f * a * (A - A_gt);                     // d/du_i (in the original orientation)
+        const float dd = gs * a * a * (1.f / 3.f);                            // d/d(dt_i)
+        // t_i receives (du_i / 2 - dd_i) from interval i and (du_{i-1} / 2 + dd_{i-1}) from interval i - 1
+        atomicAdd(d_t + (size_t)r * S + i, 0.5f * du - dd);
+        atomicAdd(d_t + (size_t)r * S + i + 1, 0.5f * du + dd);
+      }
+    }
+  }
+  if (lane == 0) d_w[(size_t)r * S] = 0.f;        // w_0 never enters (regularization_losses.py:41)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) atomicAdd(loss, gs * acc);
+}
+
+}  // namespace
+}  // namespace sparf
+
+extern "C" int sparf_distortion_fwd_bwd(int32_t R, int32_t S, const float* t, const float* w, float scale, float* loss,
+                                        float* d_w, float* d_t, sparf_stream_t stream) {
+  SPARF_REQUIRE(R >= 0 && S >= 2 && t && w && loss && d_w, "distortion: bad arguments R=%d S=%d", R, S);
+  if (R == 0) return SPARF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_t) SPARF_CHECK_CUDA(cudaMemsetAsync(d_t, 0, (size_t)R * S * sizeof(float), st));
+  distortion_kernel<<<ceil_div(R, 4), 128, 0, st>>>(R, S, t, w, scale, loss, d_w, d_t);
+  SPARF_CHECK_LAUNCH("distortion_kernel");
+  return SPARF_OK;
+}

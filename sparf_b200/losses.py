@@ -277,9 +277,37 @@ class BasePhotoandReguLoss(BaseLoss):
             if "opacity_fine" in output_dict.keys():
                 m = m + 0.5 * torch.abs(fg_mask - output_dict.opacity_fine.reshape(n_img, -1, 1)).mean()
             loss_dict.fg_mask = m
-        if opt.loss_weight.distortion is not None or opt.loss_weight.depth_patch is not None:
-            raise NotImplementedError("distortion / depth-patch regularisers (default off) are a SURVEY §8f row")
+        loss_dict = self.compute_regularization_losses(opt, output_dict, loss_dict)
         return loss_dict, {}, {}
+
+    def compute_regularization_losses(self, opt, output_dict, loss):
+        """Distortion (mip-NeRF 360) and depth-patch smoothness terms, default off (base_losses.py:162-194;
+        regularization_losses.py:20-66).  The distortion loss is one O(S) kernel per network instead of the
+        reference's [S-1, S-1] matrix per ray."""
+        if opt.loss_weight.distortion is not None:
+            strength = 1e-3 * 2
+            v = strength * ops.distortion_loss(output_dict["t"], output_dict["weights"])
+            if "weights_fine" in output_dict:
+                v = v + strength * ops.distortion_loss(output_dict["t_fine"], output_dict["weights_fine"])
+            if "distortion" in loss.keys():
+                loss["distortion"] = (loss["distortion"] + v) / 2.0
+            else:
+                loss["distortion"] = v
+        if opt.loss_weight.depth_patch is not None:
+            strength = 0.01 * 2
+
+            def patch(depths):      # a few thousand elements: plain device tensor algebra
+                B = depths.shape[0]
+                d = depths.reshape(B, -1, self.opt.depth_regu_patch_size ** 2)
+                return torch.sqrt((d[..., None] - d[..., None, :]) ** 2 + 0.001 ** 2).mean()
+            v = strength * patch(output_dict["depth"])
+            if "depth_fine" in output_dict.keys():
+                v = v + strength * patch(output_dict["depth_fine"])
+            if "depth_patch" in loss.keys():
+                loss["depth_patch"] = (loss["depth_patch"] + v) / 2.0
+            else:
+                loss["depth_patch"] = v
+        return loss
 
 
 # ------------------------------------------------------------------------------------------------

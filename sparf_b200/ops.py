@@ -392,3 +392,35 @@ class Huber2Function(torch.autograd.Function):
 def huber2(pred, target):
     """2 * mean Huber(delta=0.5)(pred - target)   (base_losses.py:155-156)."""
     return Huber2Function.apply(pred, target.expand_as(pred))
+
+
+# ------------------------------------------------------------------------------------------------
+# distortion regulariser (default off in the reference's configs)
+# ------------------------------------------------------------------------------------------------
+class DistortionFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, w):
+        L = _lib.lib()
+        t_c, w_c = _f32c(t), _f32c(w)
+        S = t_c.shape[-2] if t_c.shape[-1] == 1 else t_c.shape[-1]
+        R = t_c.numel() // S
+        loss = torch.zeros((), device=t.device)
+        d_w = torch.empty_like(w_c)
+        need_t = ctx.needs_input_grad[0]
+        d_t = torch.empty_like(t_c) if need_t else None
+        check(L.sparf_distortion_fwd_bwd(R, S, _ptr(t_c), _ptr(w_c), 1.0, _ptr(loss), _ptr(d_w), _ptr(d_t), _stream()),
+              "distortion")
+        ctx.save_for_backward(d_w, d_t if need_t else d_w)
+        ctx.need_t = need_t
+        ctx.shapes = (t.shape, w.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d_w, d_t = ctx.saved_tensors
+        return ((d_t * g).view(ctx.shapes[0]) if ctx.need_t else None), (d_w * g).view(ctx.shapes[1])
+
+
+def distortion_loss(t, w):
+    """mip-NeRF-360 distortion loss of the renderer's `t`, `weights` [B,R,S,1] (regularization_losses.py:20-48), O(S)."""
+    return DistortionFunction.apply(t, w)

@@ -267,6 +267,9 @@ CASES = {
                               depth_param="inverse", depth_range=(1, 0), peaky=True, mode="train",
                               pixels=True, pose_net=True, barf_c2f=(0.4, 0.7), progress=1.0),
     # eval mode + background compositing + hierarchical with pose grads (BARF runs fine net + poses)
+    # default-off regularisers switched on: hierarchical, distortion (both nets) + depth-patch terms
+    "c8_hier_regularisers": dict(seed=8, B=2, H=24, W=32, n_rays=24, S=64, S_fine=64, fine=True,
+                                 depth_range=(1.0, 4.5), peaky=True, mode="train", regularisers=True),
     "c5_hier_pose_bg": dict(seed=5, B=2, H=24, W=32, n_rays=16, S=64, S_fine=64, fine=True,
                             depth_range=(0.8, 4.0), peaky=True, mode="train", pose_net=True,
                             setbg=True, barf_c2f=(0.1, 0.5), progress=0.3, sigma_bias=-0.5),
@@ -296,6 +299,9 @@ def case_inputs(name):
     sd = det_weights(opt, c["seed"], peaky=c["peaky"], progress=c.get("progress"), sigma_bias=sb)
     sd_fine = det_weights(opt, c["seed"] + 77, peaky=c["peaky"], progress=c.get("progress"), sigma_bias=sb) \
         if c["fine"] else None
+    if c.get("regularisers"):
+        opt.loss_weight.distortion = 0
+        opt.loss_weight.depth_patch = 0
     init_w2c = perturb_poses(data.pose, c["seed"]) if c.get("pose_net") else None
     depth_max = None
     if c.get("to_max"):

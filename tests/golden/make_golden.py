@@ -113,6 +113,10 @@ def run_case(name):
         loss_mod = BasePhotoandReguLoss(opt, net, train_data=None, device=dev)
         loss_dict, _, _ = loss_mod.compute_loss(opt, data, out, iteration=10, mode=c["mode"])
         loss = loss_dict.render
+        if c.get("regularisers"):   # base_losses.py:162-194 through the reference's own module
+            loss = loss + loss_dict.distortion + loss_dict.depth_patch
+            extra = {"loss_render": loss_dict.render, "loss_distortion": loss_dict.distortion,
+                     "loss_depth_patch": loss_dict.depth_patch}
     else:
         loss = 0
         for suf in ([""] + (["_fine"] if "rgb_fine" in out else [])):
@@ -126,6 +130,9 @@ def run_case(name):
         if isinstance(v, torch.Tensor) and k not in ("ray_idx", "idx_img_rendered"):
             out_npz["out_" + k] = v.detach().numpy()
     out_npz["loss"] = np.float64(loss.item())
+    if c.get("regularisers"):
+        for k, v in extra.items():
+            out_npz[k] = np.float64(v.item())
     for i, r in enumerate(rec.rand_calls):
         out_npz["rand_%d" % i] = r.numpy()
     for i, r in enumerate(rec.randn_calls):

@@ -59,6 +59,10 @@ def replay_oracle(name, dtype=torch.float32):
                    depth_max=depth_max.to(dtype) if depth_max is not None else None)
     if pixels is None and not c.get("to_max"):
         loss = O.photometric_loss(out, data.image.to(dtype), ray_idx)
+        if c.get("regularisers"):
+            reg = O.regularization_losses(out, True, True, opt.depth_regu_patch_size)
+            loss = loss + reg["distortion"] + reg["depth_patch"]
+            out["loss_distortion"], out["loss_depth_patch"] = reg["distortion"].detach(), reg["depth_patch"].detach()
     else:
         loss = linear_probe_loss(out)
     loss.backward()
@@ -189,6 +193,12 @@ def replay_graph(name, engine="simt_fp32"):
             out = net.render_image_at_specific_rays(opt, data, iter=10, ray_idx=ray_idx, mode=c["mode"])
     if pixels is None and not c.get("to_max"):
         loss = O.photometric_loss(out, data.image, ray_idx)   # the loss formula is the checker's, the render is ours
+        if c.get("regularisers"):   # ... except the regularisers, whose product path (kernel + Loss mirror) is under test
+            from sparf_b200.losses import BasePhotoandReguLoss
+            mod = BasePhotoandReguLoss(opt, net, train_data=None, device=data.image.device)
+            reg = mod.compute_regularization_losses(opt, out, {})
+            loss = loss + reg["distortion"] + reg["depth_patch"]
+            out["loss_distortion"], out["loss_depth_patch"] = reg["distortion"].detach(), reg["depth_patch"].detach()
     else:
         loss = linear_probe_loss(out)
     loss.backward()

@@ -84,7 +84,9 @@ def test_mlp_and_composite_stage(name, engine):
         else:
             pred = nerf.forward_samples(opt, center, ray, t, mode=c["mode"])
         pred = nerf.composite(opt, ray, pred, t)
-        tol = 2e-5
+        # fp32 engine: the reference's op order, 2e-5; tcgen05 3-pass fp16 split: fp32-level products in a different
+        # summation order, measured <= 3e-5 against the fp32 engine (tests/test_tc_engine.py)
+        tol = 2e-5 if engine == "simt_fp32" else 3e-5
         if common.CASES[name].get("depth_param", "metric") == "inverse":
             # inverse depth reaches t ~ 256: the top encoding bands see arguments ~1e5 where one fp32 ulp
             # is ~1e-2 rad, so ANY difference in accumulation order is amplified to ~1e-3 downstream
@@ -144,7 +146,8 @@ def test_graph_end_to_end_vs_reference(name, engine):
     # (tests/test_tc_engine.py::test_tc_backward_matches_simt measures both engines against fp64): the SIMT
     # engine shares the reference's op order and lands closer to IT; the tcgen05 engine is equally close to
     # the truth but not to the reference's particular rounding.
-    gtol = 0.25 if "inverse" in name else (5e-3 if engine == "simt_fp32" else 6e-2)
+    # (c8: with the Charbonnier / distortion terms the reference's fp32 gradient is itself 1.2e-1 from the fp64 one)
+    gtol = 0.25 if "inverse" in name else (6e-2 if (engine != "simt_fp32" or common.CASES[name].get("regularisers")) else 5e-3)
     worst = check_grads(grads, gold, tol=gtol)
     print(name, engine, {k: "%.1e" % v for k, v in report.items()}, "worst grad %.1e" % worst)
 
