@@ -201,6 +201,8 @@ int sparf_adam_step(int64_t n, float* param, float* grad, float* exp_avg, float*
  * descriptors, bulk copy, TMEM): D[128,128] = bf16(A[128,K]) * bf16(B[128,K])^T, K in {64,...,256}.
  * `packed` is >= 128*K*2 bytes of scratch.  Used by tests/test_tc_engine.py. */
 int sparf_tc_selftest(const float* A, const float* B, int32_t K, void* packed, float* D, sparf_stream_t stream);
+/* Same GEMM with the A operand written to and read from tensor memory (tcgen05.st, tcgen05.mma with A in TMEM). */
+int sparf_tc_selftest_ts(const float* A, const float* B, int32_t K, void* packed, float* D, sparf_stream_t stream);
 /* Same for the weight-gradient shape: D[128,128] = G[rows,128]^T X[rows,128] through MN-major descriptors. */
 int sparf_tc_selftest_tn(const float* G, const float* X, int32_t rows, float* D, sparf_stream_t stream);
 

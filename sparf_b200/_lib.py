@@ -57,6 +57,7 @@ _SIGNATURES = {
     "sparf_distortion_fwd_bwd": (c_int32, [c_int32, c_int32, _P, _P, c_float, _P, _P, _P, _P]),
     "sparf_adam_step": (c_int32, [c_int64, _P, _P, _P, _P, _P, _P] + [ctypes.c_double] * 7 + [_P]),
     "sparf_tc_selftest": (c_int32, [_P, _P, c_int32, _P, _P, _P]),
+    "sparf_tc_selftest_ts": (c_int32, [_P, _P, c_int32, _P, _P, _P]),
     "sparf_tc_selftest_tn": (c_int32, [_P, _P, c_int32, _P, _P]),
     "sparf_tc_bulkcopy_probe": (c_int32, [_P, ctypes.c_uint32, c_int32, ctypes.c_uint32, c_int32, c_int32, _P, _P]),
 }

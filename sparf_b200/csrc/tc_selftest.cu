@@ -18,8 +18,10 @@ __global__ void selftest_pack_kernel(const float* __restrict__ B, int K, uint8_t
   *reinterpret_cast<__nv_bfloat16*>(packed + (size_t)kb * 16384 + sw128_offset(n, kl)) = v;
 }
 
+// a_in_tmem: the A operand is written to tensor memory with tcgen05.st (columns 128..) and consumed from there
+// (the operand path planned for the chain kernels: no shared-memory A blocks, no proxy fence in the epilogue)
 __global__ void __launch_bounds__(128) selftest_gemm_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Bpacked,
-                                                             int K, float* __restrict__ D) {
+                                                             int K, float* __restrict__ D, int a_in_tmem) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nkb = K / kBlockK;
@@ -35,8 +37,25 @@ __global__ void __launch_bounds__(128) selftest_gemm_kernel(const float* __restr
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(&tmem_base_s, 128);
+    tmem_alloc(&tmem_base_s, 256);
     tmem_relinquish();
+  }
+  if (a_in_tmem) {
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t a_base = tmem_base_s + 128u + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {       // 16 columns = 32 consecutive K elements of this thread's row
+      uint32_t w[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float a0 = A[(size_t)tid * K + 2 * (c0 + e)], a1 = A[(size_t)tid * K + 2 * (c0 + e) + 1];
+        __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);      // low half = even K element
+        w[e] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      tmem_st16(a_base + (uint32_t)c0, w);
+    }
+    tmem_st_wait();
   }
   // A: thread = row, generic 16-byte stores of 8 bf16 at the swizzled position
   for (int kb = 0; kb < nkb; ++kb) {
@@ -67,7 +86,8 @@ __global__ void __launch_bounds__(128) selftest_gemm_kernel(const float* __restr
       for (int ks = 0; ks < 4; ++ks) {
         uint64_t da = make_smem_desc(smem_u32(sA + (size_t)kb * 16384) + ks * 32);
         uint64_t db = make_smem_desc(smem_u32(sB + (size_t)kb * 16384) + ks * 32);
-        umma_ss(tmem_base, da, db, idesc, (kb | ks) != 0);
+        if (a_in_tmem) umma_ts(tmem_base, tmem_base + 128u + (uint32_t)(kb * 32 + ks * 8), db, idesc, (kb | ks) != 0);
+        else umma_ss(tmem_base, da, db, idesc, (kb | ks) != 0);
       }
     }
     umma_commit(&bar_mma);
@@ -83,7 +103,7 @@ __global__ void __launch_bounds__(128) selftest_gemm_kernel(const float* __restr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // "TN" GEMM with MN-major operands (the weight-gradient shape):
@@ -175,7 +195,20 @@ extern "C" int sparf_tc_selftest(const float* A, const float* B, int32_t K, void
   SPARF_CHECK_LAUNCH("selftest_pack_kernel");
   size_t smem = (size_t)2 * (K / 64) * 16384 + 1024;
   SPARF_CHECK_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  selftest_gemm_kernel<<<1, 128, smem, st>>>(A, (const uint8_t*)packed, K, D);
+  selftest_gemm_kernel<<<1, 128, smem, st>>>(A, (const uint8_t*)packed, K, D, 0);
+  SPARF_CHECK_LAUNCH("selftest_gemm_kernel");
+  return SPARF_OK;
+}
+
+// Same GEMM with the A operand in tensor memory (tcgen05.st + tcgen05.mma [d], [a], b-desc).
+extern "C" int sparf_tc_selftest_ts(const float* A, const float* B, int32_t K, void* packed, float* D, sparf_stream_t stream) {
+  SPARF_REQUIRE(K % 64 == 0 && K >= 64 && K <= 256, "tc_selftest_ts: K=%d", K);
+  cudaStream_t st = (cudaStream_t)stream;
+  selftest_pack_kernel<<<ceil_div(128 * K, 256), 256, 0, st>>>(B, K, (uint8_t*)packed);
+  SPARF_CHECK_LAUNCH("selftest_pack_kernel");
+  size_t smem = (size_t)2 * (K / 64) * 16384 + 1024;
+  SPARF_CHECK_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_gemm_kernel<<<1, 128, smem, st>>>(A, (const uint8_t*)packed, K, D, 1);
   SPARF_CHECK_LAUNCH("selftest_gemm_kernel");
   return SPARF_OK;
 }

@@ -31,6 +31,24 @@ def test_tcgen05_selftest_gemm_exact(K):
     assert torch.equal(D, ref), (D - ref).abs().max().item()
 
 
+@pytest.mark.parametrize("K", [64, 128, 256])
+def test_tcgen05_selftest_a_operand_in_tmem(K):
+    """Same exact-integer GEMM with the A operand written to tensor memory by tcgen05.st and consumed from there
+    (lane = row, column c = K elements 2c, 2c+1; +8 columns per K16 step)."""
+    from sparf_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cpu").manual_seed(100 + K)
+    A = torch.randint(-4, 5, (128, K), generator=g).float().cuda()
+    B = torch.randint(-4, 5, (128, K), generator=g).float().cuda()
+    packed = torch.zeros(128 * K * 2, dtype=torch.uint8, device="cuda")
+    D = torch.full((128, 128), -777.0, device="cuda")
+    _lib.check(L.sparf_tc_selftest_ts(_p(A), _p(B), K, _p(packed), _p(D), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "tc_selftest_ts")
+    torch.cuda.synchronize()
+    ref = A @ B.t()
+    assert torch.equal(D, ref), (D - ref).abs().max().item()
+
+
 def _rand_problem(R, S, seed=0, c2f=None, peaky=True):
     import common
     from sparf_b200 import ops
