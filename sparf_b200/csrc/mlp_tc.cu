@@ -51,7 +51,7 @@ constexpr int kTileM = 128;
 constexpr int kStages = 3;         // weight-ring stages of the forward kernel
 constexpr int kBwdStages = 6;      // ... of the dgrad kernel: its ring takes everything between the activations and the
                                    // barriers (encoder blocks, forward ring, bias / small-weight tables it does not use)
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 10;
 constexpr int kChunkBytes = 16384;  // one [128 x 64] 16-bit operand block
 constexpr int kEpiWarps = 16;       // 4 TMEM lane quadrants x 4 column quarters of every 64-column block
 constexpr int kEpiCols = 16;        // columns per epilogue warp and block
@@ -511,14 +511,17 @@ __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& 
     twait(tr, 2, &s.w_full[stage], phase);
     trace_event(tr.n, 3);
     tc_fence_after();
-    const uint32_t b_addr = ring_addr + stage * kChunkBytes;
+    // descriptor of K step ks = base descriptor + 2 ks in the 16-byte start-address field (everything lies below
+    // 256 KB: no carry), upper word constant: one add per operand instead of the full bit-field assembly
+    const uint64_t db0 = make_smem_desc(ring_addr) + (uint64_t)(stage * (kChunkBytes >> 4));
+    const uint64_t dah0 = make_smem_desc(a_hi), dal0 = make_smem_desc(a_lo);
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t db = make_smem_desc(b_addr + ks * 32);
+        const uint64_t db = db0 + (uint64_t)(2 * ks);
         const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
-        umma_ss(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
-        if (part == 0 && passes != 1) umma_ss(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+        umma_ss(d_addr, dah0 + (uint64_t)(2 * ks), db, idesc, acc);
+        if (part == 0 && passes != 1) umma_ss(d_addr, dal0 + (uint64_t)(2 * ks), db, idesc, 1u);
       }
       trace_event(tr.n, 4);
       umma_commit(&s.w_empty[stage]);   // frees the ring slot when these MMAs have read it
@@ -840,14 +843,46 @@ __device__ __forceinline__ void chain_issue_pair256(const ChainSmem& s, uint32_t
     mbar_wait_two(&s.w_full[stage], phase, &s.w_full[stage + 1], phase);
     trace_toc(tr, 2, t0);
     tc_fence_after();
-    const uint32_t b_addr = ring_addr + stage * kChunkBytes;
+    const uint64_t db0 = make_smem_desc(ring_addr) + (uint64_t)(stage * (kChunkBytes >> 4));
+    const uint64_t dah0 = make_smem_desc(a_hi), dal0 = make_smem_desc(a_lo);
     if (elect_one()) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t db = make_smem_desc(b_addr + ks * 32);
+        const uint64_t db = db0 + (uint64_t)(2 * ks);
         const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
-        umma_ss(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
-        if (part == 0) umma_ss(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
+        umma_ss(d_addr, dah0 + (uint64_t)(2 * ks), db, idesc, acc);
+        if (part == 0) umma_ss(d_addr, dal0 + (uint64_t)(2 * ks), db, idesc, 1u);
+      }
+      umma_commit(&s.w_empty[stage]);
+      umma_commit(&s.w_empty[stage + 1]);
+    }
+    __syncwarp();
+    stage += 2;
+    if (stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
+  }
+}
+
+// Same with the A operand in tensor memory (columns a_hi_t / a_lo_t of this K block, +8 columns per K16 step): the MMA
+// fetches only B from shared memory and the epilogue hands activations over with tcgen05.st instead of swizzled
+// st.shared + fence.proxy.async.
+__device__ __forceinline__ void chain_issue_pair256_ts(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi_t,
+                                                       uint32_t a_lo_t, uint32_t d_addr, uint32_t idesc, bool first_kb, Trace& tr) {
+  const uint32_t ring_addr = smem_u32(s.ring);
+  for (int part = 0; part < 2; ++part) {
+    long long t0 = trace_tic();
+    mbar_wait_two(&s.w_full[stage], phase, &s.w_full[stage + 1], phase);
+    trace_toc(tr, 2, t0);
+    tc_fence_after();
+    // descriptor of K step ks = descriptor of the stage + 2 ks in its 16-byte start-address field (no carry: the ring
+    // lies below 256 KB), upper word constant: one add per MMA instead of the full bit-field assembly
+    const uint64_t db0 = make_smem_desc(ring_addr) + (uint64_t)(stage * (kChunkBytes >> 4));
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t db = db0 + (uint64_t)(2 * ks);
+        const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
+        umma_ts(d_addr, a_hi_t + ks * 8, db, idesc, acc);
+        if (part == 0) umma_ts(d_addr, a_lo_t + ks * 8, db, idesc, 1u);
       }
       umma_commit(&s.w_empty[stage]);
       umma_commit(&s.w_empty[stage + 1]);
@@ -861,15 +896,22 @@ __device__ __forceinline__ void chain_issue_pair256(const ChainSmem& s, uint32_t
 // ------------------------------------------------------------------------------------------------
 // the fused input-gradient (dgrad) kernel: dL/dz chain from the colour head to layer 0
 // ------------------------------------------------------------------------------------------------
-template <bool kPair>
+// kTmemA (stand-alone CTA only): TMEM = [0,256) ONE accumulator | [256,384) A hi | [384,512) A lo (32 columns per K block).
+// The epilogue loads its whole share of the accumulator into registers first and hands the accumulator back at once,
+// so a single accumulator still lets layer l+1's MMAs overlap layer l's epilogue.
+template <bool kPair, bool kTmemA = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdParams p) {
+  static_assert(!(kPair && kTmemA), "the TMEM-operand variant is for stand-alone CTAs");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // shared-memory map of this kernel: activations (8 blocks) | 6-stage weight ring | barriers.  The density row and the
   // 128 -> 3 colour weights (2.5 KB, read by every thread) come from global memory through L1.
   const float* __restrict__ s_w7r0 = p.w7;
   const float* __restrict__ s_w9 = p.w9;
-  const ChainSmem cs = chain_carve(smem, kOffEnc, kBwdStages, kOffBarBwd);
+  // kTmemA: the activation blocks are no MMA operands any more, only a staging area for the image stores: two rotating
+  // (hi, lo) block pairs (64 KB) are enough and the weight ring takes the rest: 10 stages = 5 [256 x 64] operands
+  const ChainSmem cs = kTmemA ? chain_carve(smem, kOffAct + 4 * kChunkBytes, 10, kOffBarBwd)
+                              : chain_carve(smem, kOffEnc, kBwdStages, kOffBarBwd);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
@@ -930,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
       Trace tr; trace_begin(tr);
       for (int it = 0; it < my_tiles; ++it) {
         for (int bl = 0; bl < kNumBwdLayers; ++bl) {
-          const int buf = bl & 1;
+          const int buf = kTmemA ? 0 : (bl & 1);
           twait(tr, 0, &cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
           ++d_cnt[buf];
           tc_fence_after();
@@ -939,8 +981,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             twait(tr, 1, &cs.a_ready[kbi], a_cnt[kbi] & 1);
             ++a_cnt[kbi];
             tc_fence_after();
-            const uint32_t a_hi = act_addr + kbi * kChunkBytes, a_lo = act_addr + (4 + kbi) * kChunkBytes;
-            chain_issue_pair256(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, tr);
+            if (kTmemA) {
+              chain_issue_pair256_ts(cs, stage, phase, tmem_base + 256u + (uint32_t)(kbi * 32),
+                                     tmem_base + 384u + (uint32_t)(kbi * 32), tmem_base, idesc, kbi == 0, tr);
+            } else {
+              const uint32_t a_hi = act_addr + kbi * kChunkBytes, a_lo = act_addr + (4 + kbi) * kChunkBytes;
+              chain_issue_pair256(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, tr);
+            }
           }
           if (elect_one()) umma_commit(&cs.d_full[buf]);
           __syncwarp();
@@ -960,16 +1007,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         const int nblk = step == 0 ? 2 : 4;
         const int t_out = step == 0 ? T_GHID : (step == 1 ? T_G7F : t_g(8 - step));
         for (int j = 0; j < nblk; ++j) {
+          // stand-alone blocks: barrier j, write number n of block j.  kTmemA: two rotating staging slots, q = running
+          // index of the (tile, step, block) writes, slot = q & 1, k = q >> 1 its per-slot sequence number
+          const uint32_t q = 34u * (uint32_t)it + (step == 0 ? (uint32_t)j : 2u + 4u * (uint32_t)(step - 1) + (uint32_t)j);
           const uint32_t n = j < 2 ? 9u * (uint32_t)it + (uint32_t)step : 8u * (uint32_t)it + (uint32_t)step - 1u;
-          mbar_wait(&cs.g_ready[j], n & 1);
+          const int bi = kTmemA ? (int)(q & 1u) : j;
+          const uint8_t* src_hi = kTmemA ? smem + kOffAct + (size_t)bi * 2 * kChunkBytes : act_hi + (size_t)j * kChunkBytes;
+          const uint8_t* src_lo = kTmemA ? src_hi + kChunkBytes : act_lo + (size_t)j * kChunkBytes;
+          mbar_wait(&cs.g_ready[bi], (kTmemA ? (q >> 1) : n) & 1);
           if (elect_one()) {
             if (tile_ok) {
-              bulk_s2g(p.img.at(t_out, tile, j, 0), act_hi + (size_t)j * kChunkBytes, kChunkBytes);
-              bulk_s2g(p.img.at(t_out, tile, j, 1), act_lo + (size_t)j * kChunkBytes, kChunkBytes);
+              bulk_s2g(p.img.at(t_out, tile, j, 0), src_hi, kChunkBytes);
+              bulk_s2g(p.img.at(t_out, tile, j, 1), src_lo, kChunkBytes);
               bulk_commit_group();
               bulk_wait_read_all();
             }
-            mbar_arrive(&cs.s_free[j]);
+            mbar_arrive(&cs.s_free[bi]);
           }
           __syncwarp();
         }
@@ -1025,17 +1078,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         }
         Split16 sp;
         split16<false>(f, sp);
-        const uint32_t n = 9u * (uint32_t)it;
-        if (n > 0) mbar_wait(&cs.s_free[j], (n - 1) & 1);
-        store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
-        if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) { chain_arrive<kPair>(&cs.a_ready[j], rank); mbar_arrive(&cs.g_ready[j]); }
+        if (kTmemA) {   // operand for the MMA: tensor memory; the shared-memory copy below only feeds the image store
+          tmem_st8(tmem_base + t_lane + 256u + (uint32_t)(j * 32 + cq * 8), sp.hi);
+          tmem_st8(tmem_base + t_lane + 384u + (uint32_t)(j * 32 + cq * 8), sp.lo);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+        }
+        if (kTmemA) {
+          const uint32_t q = 34u * (uint32_t)it + (uint32_t)j, k = q >> 1;
+          const int slot = (int)(q & 1u);
+          uint8_t* st_hi = smem + kOffAct + (size_t)slot * 2 * kChunkBytes;
+          if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
+          store16(sp, row, cq * kEpiCols, st_hi, st_hi + kChunkBytes);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
+        } else {
+          const uint32_t n = 9u * (uint32_t)it;
+          if (n > 0) mbar_wait(&cs.s_free[j], (n - 1) & 1);
+          store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
+          if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { chain_arrive<kPair>(&cs.a_ready[j], rank); mbar_arrive(&cs.g_ready[j]); }
+        }
       }
 
       // ---------------- backward layers
       for (int bl = 0; bl < kNumBwdLayers; ++bl) {
-        const int buf = bl & 1;
+        const int buf = kTmemA ? 0 : (bl & 1);
         // ReLU mask of the forward activation this gradient flows into: feat (bl 0), h6 (bl 1), ... h0 (bl 7)
         long long tt = trace_tic();
         const uint2 mk = *p.img.mask_at(tile, bl == 0 ? 7 : 7 - bl, row, cq);
@@ -1045,16 +1117,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         ++d_cnt[buf];
         tc_fence_after();
         uint32_t vn[16];                            // accumulator columns of the NEXT block, loaded one block ahead
-        tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
-#pragma unroll 1
+        uint32_t va[kTmemA ? 4 : 1][16];            // kTmemA: this thread's whole share of the accumulator
+        if (kTmemA) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tmem_ld16(tmem_base + t_lane + (uint32_t)(j * 64 + cq * kEpiCols), va[j]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cs.d_empty[0]);   // the (single) accumulator is free for the next layer's MMAs
+        } else {
+          tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
+        }
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t v[16];
           const int col0 = j * 64 + cq * kEpiCols;
           long long tt2 = trace_tic();
-          tmem_ld_wait();
+          if (kTmemA) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = vn[i];
-          if (j + 1 < 4) tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0 + 64), vn);
+            for (int i = 0; i < 16; ++i) v[i] = va[j][i];
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = vn[i];
+            if (j + 1 < 4) tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0 + 64), vn);
+          }
           trace_toc(tr, 2, tt2);
           float f[16];
           const uint32_t mask = (masks[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
@@ -1067,21 +1154,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           const bool chain = bl != kNumBwdLayers - 1;   // G0 is only saved, nothing consumes it on-chip
           Split16 sp;
           split16<false>(f, sp);
-          const uint32_t n = j < 2 ? 9u * (uint32_t)it + (uint32_t)bl + 1u : 8u * (uint32_t)it + (uint32_t)bl;
+          if (kTmemA && chain) {
+            tmem_st8(tmem_base + t_lane + 256u + (uint32_t)(j * 32 + cq * 8), sp.hi);
+            tmem_st8(tmem_base + t_lane + 384u + (uint32_t)(j * 32 + cq * 8), sp.lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+          }
           long long tt3 = trace_tic();
-          if (n > 0) mbar_wait(&cs.s_free[j], (n - 1) & 1);
-          trace_toc(tr, 3, tt3);
-          store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
-          if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (chain) chain_arrive<kPair>(&cs.a_ready[j], rank);
-            mbar_arrive(&cs.g_ready[j]);
+          if (kTmemA) {
+            const uint32_t q = 34u * (uint32_t)it + 2u + 4u * (uint32_t)bl + (uint32_t)j, k = q >> 1;
+            const int slot = (int)(q & 1u);
+            uint8_t* st_hi = smem + kOffAct + (size_t)slot * 2 * kChunkBytes;
+            if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
+            trace_toc(tr, 3, tt3);
+            store16(sp, row, cq * kEpiCols, st_hi, st_hi + kChunkBytes);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
+          } else {
+            const uint32_t n = j < 2 ? 9u * (uint32_t)it + (uint32_t)bl + 1u : 8u * (uint32_t)it + (uint32_t)bl;
+            if (n > 0) mbar_wait(&cs.s_free[j], (n - 1) & 1);
+            trace_toc(tr, 3, tt3);
+            store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
+            if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (chain) chain_arrive<kPair>(&cs.a_ready[j], rank);
+              mbar_arrive(&cs.g_ready[j]);
+            }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
+        if (!kTmemA) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
+        }
       }
     }
     if (lane == 0 && (e == 0 || e == kEpiWarps - 1)) trace_end(tr, e == 0 ? 2 : 3);
@@ -1782,6 +1891,7 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_encgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgSmem + 1024));
     attr_set = true;
@@ -1962,7 +2072,9 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
         return SPARF_ERR_CUDA;
       }
     } else {
-      tc_mlp_dgrad_kernel<false><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
+      static const bool tmem_a = getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '1';
+      if (tmem_a) tc_mlp_dgrad_kernel<false, true><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
+      else tc_mlp_dgrad_kernel<false><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
       TRACE_DUMP("dgrad");
     }
     SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
