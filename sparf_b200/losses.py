@@ -81,7 +81,7 @@ def generate_pair_list(n_views: int) -> torch.Tensor:
 def get_nearest_pose_ids(tar_pose_c2w: np.ndarray, ref_poses_c2w: np.ndarray, tar_id: int) -> int:
     """Closest other camera by the angle between camera-position vectors (data_utils.py:267-311,
     angular_dist_method='vector', scene centre at the origin)."""
-    tiny = 1e-10 if False else 1e-6
+    tiny = 1e-6   # TINY_NUMBER, data_utils.py:27
     a = tar_pose_c2w[:3, 3][None].repeat(len(ref_poses_c2w), 0)
     b = ref_poses_c2w[:, :3, 3]
     au = a / (np.linalg.norm(a, axis=1, keepdims=True) + tiny)
