@@ -2072,7 +2072,8 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
         return SPARF_ERR_CUDA;
       }
     } else {
-      static const bool tmem_a = getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '1';
+      // A operand in tensor memory (default; SPARF_TC_TMEMA=0 selects the shared-memory-operand kernel): 294 vs 360 us
+      static const bool tmem_a = !(getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '0');
       if (tmem_a) tc_mlp_dgrad_kernel<false, true><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
       else tc_mlp_dgrad_kernel<false><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
       TRACE_DUMP("dgrad");
