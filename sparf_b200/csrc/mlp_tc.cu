@@ -160,6 +160,7 @@ __host__ __device__ inline int enc_ref_col(int ic) {
 //   backward: for bl: for kb: for nh: for part: chunk [128 (n = in)  x 64 (k = out)]         = W[k][n]
 // ------------------------------------------------------------------------------------------------
 struct PackParams {
+  int order;               // 0: chunks ordered (K block, N half, part); 1: (K block, part, N half) = N-256 pairing
   const float* w[9];   // trunk 0..7, head 0
   uint8_t* packed;
 };
@@ -176,6 +177,7 @@ __global__ void pack_weights_kernel(PackParams pp) {
   }
   int rel = chunk - base;
   int part = rel & 1, nh = (rel >> 1) % layer_nh(l), kbi = (rel >> 1) / layer_nh(l);
+  if (pp.order == 1 && layer_nh(l) == 2) { nh = rel & 1; part = (rel >> 1) & 1; kbi = rel >> 2; }
   const bool enc = kb_is_enc(l, kbi);
   const int ldw = l == 0 ? 63 : (l == 4 ? 319 : (l == 8 ? 283 : 256));
   const float* W = pp.w[l];
@@ -289,6 +291,11 @@ __device__ __forceinline__ void store16_image(const Split16& v, int row, int col
     st_global_256(g_hi + off, v.hi[0], v.hi[1], v.hi[2], v.hi[3], v.hi[4], v.hi[5], v.hi[6], v.hi[7]);
     st_global_256(g_lo + off, v.lo[0], v.lo[1], v.lo[2], v.lo[3], v.lo[4], v.lo[5], v.lo[6], v.lo[7]);
   }
+}
+__device__ __forceinline__ void store16_part(const uint32_t (&w)[8], int row, int col0, uint8_t* blk) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    *reinterpret_cast<uint4*>(blk + sw128_offset(row, col0 + c * 8)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
 __device__ __forceinline__ void store16(const Split16& v, int row, int col0, uint8_t* b_hi, uint8_t* b_lo) {
 #pragma unroll
@@ -533,304 +540,6 @@ __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// the fused forward kernel
-// ------------------------------------------------------------------------------------------------
-// kPair: launched as clusters of 2 CTAs; each CTA keeps its own 128-row tile (A operand, accumulator lanes,
-// epilogue) but the pair's leader issues ONE tcgen05.mma.cta_group::2 (M = 256) per step with the B operand
-// split across the two SMs, which halves the weight bytes every SM has to pull per unit of tensor work.
-template <bool kF16, bool kPair>
-__global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
-  float* s_w7r0 = reinterpret_cast<float*>(smem + kOffW7r0);
-  float* s_w9 = reinterpret_cast<float*>(smem + kOffW9);
-  float* s_misc = reinterpret_cast<float*>(smem + kOffMisc);   // [0]=b7[0], [1..3]=b9, [8..23]=c2f weights
-  float* s_part = reinterpret_cast<float*>(smem + kOffPart);   // [cq - 1][row][4]
-  const ChainSmem cs = chain_carve(smem, kOffRing, kStages);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  // ---- one-time setup
-  for (int i = tid; i < 8 * 256; i += kThreads) {
-    int l = i >> 8, n = i & 255;
-    s_bias[i] = p.bias[l][n + (l == 7 ? 1 : 0)];
-  }
-  for (int i = tid; i < 256; i += kThreads) s_w7r0[i] = p.w7[i];
-  for (int i = tid; i < 3 * 128; i += kThreads) s_w9[i] = p.w9[i];
-  if (tid == 0) {
-    s_misc[0] = p.bias[7][0];
-    s_misc[1] = p.b9[0]; s_misc[2] = p.b9[1]; s_misc[3] = p.b9[2];
-  }
-  if (tid < 16) s_misc[8 + tid] = tid < kL ? band_weight(p.c2f, kL, tid) : 0.f;
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  const uint8_t* my_packed = p.packed + (size_t)((kPair ? blockIdx.x / 2 : blockIdx.x) % p.ncopies) * kChunksPerTile * kChunkBytes;
-  if (tid == 32) chain_init_barriers(cs, kPair ? 2 : 1);
-  if (kPair) cluster_sync_all();     // barrier inits of both CTAs visible before any remote arrive / multicast commit
-  if (warp == 1) {
-    if (kPair) { tmem_alloc2(cs.tmem_slot, 512); tmem_relinquish2(); }
-    else { tmem_alloc(cs.tmem_slot, 512); tmem_relinquish(); }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *cs.tmem_slot, 0);   // warp-uniform for the compiler
-
-  // work items: tiles (stand-alone) or tile pairs (CTA pair: tile = 2 * pair + rank; a missing odd tile is a dummy)
-  const int n_items = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
-  const int n_workers = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
-  const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
-  const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
-
-  if (warp == 0) {
-    if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
-    else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1);
-  } else if (warp == 1 || warp == 2 + kEpiWarps) {
-    const int issuer = warp == 1 ? 0 : 1;
-    // ============================== MMA issuer ==============================
-    if (kPair && issuer != 0) {
-      // the second issuer warp has no role in a CTA pair
-    } else if (kPair && rank == 1) {
-      pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, true);   // relay "my half landed" to the leader
-    } else if (kPair) {
-      const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
-      uint32_t stage = 0, phase = 0;
-      uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
-      uint32_t d_cnt[2] = {0, 0};
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int l = 0; l < kNumLayers; ++l) {
-          const int buf = l & 1;
-          const uint32_t idesc = make_idesc(256, l == 8 ? 128 : 256, kF16 ? 0 : 1);
-          mbar_wait_cluster(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
-          ++d_cnt[buf];
-          tc_fence_after();
-          const int nkb = layer_nkb(l);
-          for (int kbi = 0; kbi < nkb; ++kbi) {
-            uint32_t a_hi, a_lo;
-            if (kb_is_enc(l, kbi)) {
-              if (l == 0) { mbar_wait_cluster(&cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
-              a_hi = enc_addr; a_lo = enc_addr + kChunkBytes;
-            } else {
-              int a = kb_act_index(l, kbi);
-              mbar_wait_cluster(&cs.a_ready[a], a_cnt[a] & 1);
-              ++a_cnt[a];
-              a_hi = act_addr + a * kChunkBytes; a_lo = act_addr + (4 + a) * kChunkBytes;
-            }
-            tc_fence_after();
-            pair_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, p.passes);
-          }
-          if (elect_one()) umma_commit2(&cs.d_full[buf]);
-          __syncwarp();
-        }
-      }
-    } else if (!kPair) {
-      const uint32_t idesc = make_idesc(128, 128, kF16 ? 0 : 1);
-      const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
-      uint32_t stage = 0, phase = 0;
-      uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
-      uint32_t d_cnt[2] = {0, 0};
-      Trace tr; trace_begin(tr);
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int l = 0; l < kNumLayers; ++l) {
-          const int buf = l & 1;
-          twait(tr, 0, &cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);   // epilogue of the previous user of this accumulator
-          ++d_cnt[buf];
-          tc_fence_after();
-          const int nkb = layer_nkb(l), nh_cnt = layer_nh(l);
-          for (int kbi = 0; kbi < nkb; ++kbi) {
-            uint32_t a_hi, a_lo;
-            if (kb_is_enc(l, kbi)) {
-              if (l == 0) { twait(tr, 1, &cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
-              a_hi = enc_addr; a_lo = enc_addr + kChunkBytes;
-            } else {
-              int a = kb_act_index(l, kbi);
-              twait(tr, 1, &cs.a_ready[a], a_cnt[a] & 1);
-              ++a_cnt[a];
-              a_hi = act_addr + a * kChunkBytes; a_lo = act_addr + (4 + a) * kChunkBytes;
-            }
-            tc_fence_after();
-            for (int nh = 0; nh < nh_cnt; ++nh)
-              chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
-                                kbi == 0, p.passes, nh_cnt == 1 ? issuer == 0 : nh == issuer, tr);
-          }
-          if (elect_one()) umma_commit(&cs.d_full[buf]);            // this warp's share of layer l's accumulator complete
-          __syncwarp();
-        }
-      }
-      if (lane == 0 && issuer == 0) trace_end(tr, 1);
-    }
-  } else if (warp < 2 + kEpiWarps) {
-    // ============================== epilogue warps ==============================
-    const int e = warp - 2;
-    const int q = warp & 3;           // TMEM lane quadrant this warp may access
-    const int cq = e >> 2;            // which 16-column quarter of every 64-column block
-    const int row = q * 32 + lane;
-    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-    uint32_t d_cnt[2] = {0, 0};
-    uint8_t* act_hi = smem + kOffAct;
-    uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
-    const float* wts = s_misc + 8;
-    Trace tr; trace_begin(tr);
-
-    for (int it = 0; it < my_tiles; ++it) {
-      const int tile = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
-      const bool tile_ok = tile < p.num_tiles;                       // false only for the dummy half of an odd pair
-      const long long m = (long long)tile * kTileM + row;
-      const bool valid = tile_ok && m < p.M;
-      const long long ray = valid ? m / p.S : 0;
-      const bool save = p.save && tile_ok;
-
-      // ---------------- positional encoding -> A_enc (internal column order: x y z 0 | (sin,cos) pairs)
-      {
-        float x[3] = {0.f, 0.f, 0.f};
-        if (valid) {
-          float tv = p.t[m];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) x[c] = add_rn(p.origins[ray * 3 + c], mul_rn(p.dirs[ray * 3 + c], tv));
-        }
-        float vals[16];
-        if (cq == 0) { vals[0] = x[0]; vals[1] = x[1]; vals[2] = x[2]; vals[3] = 0.f; }
-        const int p0 = cq == 0 ? 0 : 8 * cq - 2, np = cq == 0 ? 6 : 8, v0 = cq == 0 ? 4 : 0;   // 6 + 8 + 8 + 8 pairs
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i < np) {
-            int pr = p0 + i;
-            int c = pr / kL, j = pr - c * kL;
-            float arg = mul_rn(c == 0 ? x[0] : (c == 1 ? x[1] : x[2]), band_freq(j));
-            float sn, cs_;
-            sincosf(arg, &sn, &cs_);
-            float w = wts[j];
-            vals[v0 + 2 * i] = mul_rn(sn, w);
-            vals[v0 + 2 * i + 1] = mul_rn(cs_, w);
-          }
-        }
-        Split16 sp;
-        split16<kF16>(vals, sp);
-        store16(sp, row, cq * kEpiCols, smem + kOffEnc, smem + kOffEnc + kChunkBytes);
-        if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) chain_arrive<kPair>(&cs.a_ready[4], rank);
-        if (save) {
-          if (kF16) split16<false>(vals, sp);
-          store16_image(sp, row, cq * kEpiCols, p.img.at(T_ENC, tile, 0, 0), p.img.at(T_ENC, tile, 0, 1));
-        }
-      }
-
-      // ---------------- layers
-      for (int l = 0; l < kNumLayers; ++l) {
-        const int buf = l & 1;
-        twait(tr, 0, &cs.d_full[buf], d_cnt[buf] & 1);
-        ++d_cnt[buf];
-        tc_fence_after();
-        const int nchunk = l == 8 ? 2 : 4;
-        float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;   // density row (l == 6) or rgb rows (l == 8)
-        uint32_t mbits[2] = {0u, 0u};               // ReLU mask of this thread's 16 columns in each block
-        uint32_t vn[16];                            // accumulator columns of the NEXT block, loaded one block ahead
-        tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
-        for (int j = 0; j < nchunk; ++j) {
-          uint32_t v[16];
-          const int col0 = j * 64 + cq * kEpiCols;
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = vn[i];
-          if (j + 1 < nchunk) tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0 + 64), vn);
-          float f[16];
-          if (l < 8) {
-            const float* b = s_bias + l * 256 + col0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + b[i], 0.f);
-          } else {
-            const float* b = p.raybias + (size_t)ray * kHW + col0;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float4 bb = *reinterpret_cast<const float4*>(b + i);
-              f[i] = fmaxf(__uint_as_float(v[i]) + bb.x, 0.f);
-              f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + bb.y, 0.f);
-              f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + bb.z, 0.f);
-              f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + bb.w, 0.f);
-            }
-          }
-          if (l == 6) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) dot0 = fmaf(f[i], s_w7r0[col0 + i], dot0);
-          }
-          if (save) {
-            uint32_t m16 = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) m16 |= (f[i] > 0.f ? 1u : 0u) << i;
-            mbits[j >> 1] |= m16 << (16 * (j & 1));
-          }
-          Split16 sp;
-          if (l == 8) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              dot0 = fmaf(f[i], s_w9[col0 + i], dot0);
-              dot1 = fmaf(f[i], s_w9[128 + col0 + i], dot1);
-              dot2 = fmaf(f[i], s_w9[256 + col0 + i], dot2);
-            }
-            if (save) {   // hid image for the 128->3 head's weight gradient and its ReLU mask
-              split16<false>(f, sp);
-              store16_image(sp, row, cq * kEpiCols, p.img.at(T_HID, tile, j, 0), p.img.at(T_HID, tile, j, 1));
-            }
-          } else {
-            split16<kF16>(f, sp);
-            store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
-            if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
-            if (save) {
-              const int tsave = l == 7 ? T_FEAT : T_H0 + l;
-              if (kF16) split16<false>(f, sp);
-              store16_image(sp, row, cq * kEpiCols, p.img.at(tsave, tile, j, 0), p.img.at(tsave, tile, j, 1));
-            }
-          }
-        }
-        // accumulator drained: hand it back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
-        if (save) *p.img.mask_at(tile, l, row, cq) = make_uint2(mbits[0], mbits[1]);
-
-        if (l == 6 || l == 8) {
-          // combine the four column quarters of each row (warps q, q+4, q+8, q+12) through shared memory
-          if (cq != 0) {
-            float* pr = s_part + ((size_t)(cq - 1) * 128 + row) * 4;
-            pr[0] = dot0; pr[1] = dot1; pr[2] = dot2;
-          }
-          named_bar_sync(1, kEpiWarps * 32);
-          if (cq == 0 && valid) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const float* o = s_part + ((size_t)k * 128 + row) * 4;
-              dot0 += o[0]; dot1 += o[1]; dot2 += o[2];
-            }
-            if (l == 6) {
-              float raw = dot0 + s_misc[0];
-              float z = p.noise ? add_rn(raw, p.noise[m]) : raw;
-              p.sigma[m] = softplus_f(z);
-            } else {
-              p.rgb[m * 3 + 0] = sigmoid_f(dot0 + s_misc[1]);
-              p.rgb[m * 3 + 1] = sigmoid_f(dot1 + s_misc[2]);
-              p.rgb[m * 3 + 2] = sigmoid_f(dot2 + s_misc[3]);
-            }
-          }
-          named_bar_sync(1, kEpiWarps * 32);
-        }
-      }
-    }
-    if (lane == 0 && (e == 0 || e == kEpiWarps - 1)) trace_end(tr, e == 0 ? 2 : 3);
-  }
-
-  // ---- teardown
-  tc_fence_before();
-  __syncthreads();
-  if (kPair) cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still signal it
-  if (warp == 1) {
-    if (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // N = 256 variant for rings whose chunk order is (K block, part, N half) and whose stage count is even: the two N
 // halves of a part sit in adjacent stages, i.e. form one [256 x 64] K-major operand, and ONE M128 x N256 MMA covers
 // them.  Half the instructions and barrier round trips per unit of tensor work (one issuer warp suffices) and
@@ -890,6 +599,447 @@ __device__ __forceinline__ void chain_issue_pair256_ts(const ChainSmem& s, uint3
     __syncwarp();
     stage += 2;
     if (stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
+  }
+}
+
+// one [128 x 64] weight chunk per part against an A operand in tensor memory (the N = 128 colour-head layer)
+__device__ __forceinline__ void chain_issue_single_ts(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi_t,
+                                                      uint32_t a_lo_t, uint32_t d_addr, uint32_t idesc, bool first_kb, Trace& tr) {
+  const uint32_t ring_addr = smem_u32(s.ring);
+  for (int part = 0; part < 2; ++part) {
+    twait(tr, 2, &s.w_full[stage], phase);
+    tc_fence_after();
+    const uint64_t db0 = make_smem_desc(ring_addr) + (uint64_t)(stage * (kChunkBytes >> 4));
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t db = db0 + (uint64_t)(2 * ks);
+        const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
+        umma_ts(d_addr, a_hi_t + ks * 8, db, idesc, acc);
+        if (part == 0) umma_ts(d_addr, a_lo_t + ks * 8, db, idesc, 1u);
+      }
+      umma_commit(&s.w_empty[stage]);
+    }
+    __syncwarp();
+    if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused forward kernel
+// ------------------------------------------------------------------------------------------------
+// kPair: launched as clusters of 2 CTAs; each CTA keeps its own 128-row tile (A operand, accumulator lanes,
+// epilogue) but the pair's leader issues ONE tcgen05.mma.cta_group::2 (M = 256) per step with the B operand
+// split across the two SMs, which halves the weight bytes every SM has to pull per unit of tensor work.
+//
+// kTmemA (stand-alone CTA, 3 passes): the A operand of every layer except the encoder block lives in tensor memory.
+//   TMEM  [0,256) ONE accumulator | [256,384) A hi | [384,512) A lo (32 columns per K block)
+//   smem  [0,32K) encoder operand (hi, lo) | taping: [32K,80K) three rotating 16 KB staging slots for the bf16 tape
+//         images + an 8-stage weight ring; inference: a 10-stage ring | bias / small weights / barriers as before
+// One issuer warp (M128 x N256 MMAs over paired ring stages), the epilogue drains its whole share of the accumulator
+// into registers and frees it at once; warp 19 streams the tape images out of the staging slots with bulk copies.
+constexpr int kOffEncT = 0;
+constexpr int kOffStgT = 2 * kChunkBytes;
+constexpr int kOffRingTSave = kOffStgT + 3 * kChunkBytes, kStagesTSave = 8;
+constexpr int kOffRingTInf = 2 * kChunkBytes, kStagesTInf = 10;
+static_assert(kOffRingTSave + kStagesTSave * kChunkBytes <= kOffBias && kOffRingTInf + kStagesTInf * kChunkBytes <= kOffBias,
+              "tensor-memory-operand forward: shared-memory map");
+
+template <bool kF16, bool kPair, bool kTmemA = false>
+__global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams p) {
+  static_assert(!(kPair && kTmemA), "the TMEM-operand variant is for stand-alone CTAs");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
+  float* s_w7r0 = reinterpret_cast<float*>(smem + kOffW7r0);
+  float* s_w9 = reinterpret_cast<float*>(smem + kOffW9);
+  float* s_misc = reinterpret_cast<float*>(smem + kOffMisc);   // [0]=b7[0], [1..3]=b9, [8..23]=c2f weights
+  float* s_part = reinterpret_cast<float*>(smem + kOffPart);   // [cq - 1][row][4]
+  const ChainSmem cs = !kTmemA ? chain_carve(smem, kOffRing, kStages)
+                                : (p.save ? chain_carve(smem, kOffRingTSave, kStagesTSave) : chain_carve(smem, kOffRingTInf, kStagesTInf));
+  uint8_t* const enc_blk = smem + (kTmemA ? kOffEncT : kOffEnc);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup
+  for (int i = tid; i < 8 * 256; i += kThreads) {
+    int l = i >> 8, n = i & 255;
+    s_bias[i] = p.bias[l][n + (l == 7 ? 1 : 0)];
+  }
+  for (int i = tid; i < 256; i += kThreads) s_w7r0[i] = p.w7[i];
+  for (int i = tid; i < 3 * 128; i += kThreads) s_w9[i] = p.w9[i];
+  if (tid == 0) {
+    s_misc[0] = p.bias[7][0];
+    s_misc[1] = p.b9[0]; s_misc[2] = p.b9[1]; s_misc[3] = p.b9[2];
+  }
+  if (tid < 16) s_misc[8 + tid] = tid < kL ? band_weight(p.c2f, kL, tid) : 0.f;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint8_t* my_packed = p.packed + (size_t)((kPair ? blockIdx.x / 2 : blockIdx.x) % p.ncopies) * kChunksPerTile * kChunkBytes;
+  if (tid == 32) chain_init_barriers(cs, kPair ? 2 : 1, kTmemA ? 1 : kIssuers);
+  if (kPair) cluster_sync_all();     // barrier inits of both CTAs visible before any remote arrive / multicast commit
+  if (warp == 1) {
+    if (kPair) { tmem_alloc2(cs.tmem_slot, 512); tmem_relinquish2(); }
+    else { tmem_alloc(cs.tmem_slot, 512); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *cs.tmem_slot, 0);   // warp-uniform for the compiler
+
+  // work items: tiles (stand-alone) or tile pairs (CTA pair: tile = 2 * pair + rank; a missing odd tile is a dummy)
+  const int n_items = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
+  const int n_workers = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
+
+  if (warp == 0) {
+    if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
+    else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1);
+  } else if (warp == 1 || warp == 2 + kEpiWarps) {
+    const int issuer = warp == 1 ? 0 : 1;
+    // ============================== MMA issuer ==============================
+    if (kPair && issuer != 0) {
+      // the second issuer warp has no role in a CTA pair
+    } else if (kPair && rank == 1) {
+      pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, true);   // relay "my half landed" to the leader
+    } else if (kPair) {
+      const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
+      uint32_t stage = 0, phase = 0;
+      uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
+      uint32_t d_cnt[2] = {0, 0};
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int buf = l & 1;
+          const uint32_t idesc = make_idesc(256, l == 8 ? 128 : 256, kF16 ? 0 : 1);
+          mbar_wait_cluster(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
+          ++d_cnt[buf];
+          tc_fence_after();
+          const int nkb = layer_nkb(l);
+          for (int kbi = 0; kbi < nkb; ++kbi) {
+            uint32_t a_hi, a_lo;
+            if (kb_is_enc(l, kbi)) {
+              if (l == 0) { mbar_wait_cluster(&cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
+              a_hi = enc_addr; a_lo = enc_addr + kChunkBytes;
+            } else {
+              int a = kb_act_index(l, kbi);
+              mbar_wait_cluster(&cs.a_ready[a], a_cnt[a] & 1);
+              ++a_cnt[a];
+              a_hi = act_addr + a * kChunkBytes; a_lo = act_addr + (4 + a) * kChunkBytes;
+            }
+            tc_fence_after();
+            pair_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, p.passes);
+          }
+          if (elect_one()) umma_commit2(&cs.d_full[buf]);
+          __syncwarp();
+        }
+      }
+    } else if (kTmemA) {
+      if (issuer == 0) {
+        const uint32_t idesc256 = make_idesc(128, 256, kF16 ? 0 : 1), idesc128 = make_idesc(128, 128, kF16 ? 0 : 1);
+        const uint32_t enc_addr = smem_u32(enc_blk);
+        uint32_t stage = 0, phase = 0;
+        uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
+        uint32_t d_cnt = 0;
+        Trace tr; trace_begin(tr);
+        for (int it = 0; it < my_tiles; ++it) {
+          for (int l = 0; l < kNumLayers; ++l) {
+            twait(tr, 0, &cs.d_empty[0], (d_cnt & 1) ^ 1);          // every epilogue warp has the previous accumulator in registers
+            ++d_cnt;
+            tc_fence_after();
+            const int nkb = layer_nkb(l);
+            for (int kbi = 0; kbi < nkb; ++kbi) {
+              if (kb_is_enc(l, kbi)) {                              // encoder block: operand in shared memory
+                if (l == 0) { twait(tr, 1, &cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
+                tc_fence_after();
+                chain_issue_pair256(cs, stage, phase, enc_addr, enc_addr + kChunkBytes, tmem_base, idesc256, kbi == 0, tr);
+              } else {
+                const int a = kb_act_index(l, kbi);
+                twait(tr, 1, &cs.a_ready[a], a_cnt[a] & 1);
+                ++a_cnt[a];
+                tc_fence_after();
+                const uint32_t a_hi_t = tmem_base + 256u + (uint32_t)(a * 32), a_lo_t = tmem_base + 384u + (uint32_t)(a * 32);
+                if (l == 8) chain_issue_single_ts(cs, stage, phase, a_hi_t, a_lo_t, tmem_base, idesc128, kbi == 0, tr);
+                else chain_issue_pair256_ts(cs, stage, phase, a_hi_t, a_lo_t, tmem_base, idesc256, kbi == 0, tr);
+              }
+            }
+            if (elect_one()) umma_commit(&cs.d_full[0]);
+            __syncwarp();
+          }
+        }
+        if (lane == 0) trace_end(tr, 1);
+      }
+    } else if (!kPair) {
+      const uint32_t idesc = make_idesc(128, 128, kF16 ? 0 : 1);
+      const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
+      uint32_t stage = 0, phase = 0;
+      uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
+      uint32_t d_cnt[2] = {0, 0};
+      Trace tr; trace_begin(tr);
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int buf = l & 1;
+          twait(tr, 0, &cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);   // epilogue of the previous user of this accumulator
+          ++d_cnt[buf];
+          tc_fence_after();
+          const int nkb = layer_nkb(l), nh_cnt = layer_nh(l);
+          for (int kbi = 0; kbi < nkb; ++kbi) {
+            uint32_t a_hi, a_lo;
+            if (kb_is_enc(l, kbi)) {
+              if (l == 0) { twait(tr, 1, &cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
+              a_hi = enc_addr; a_lo = enc_addr + kChunkBytes;
+            } else {
+              int a = kb_act_index(l, kbi);
+              twait(tr, 1, &cs.a_ready[a], a_cnt[a] & 1);
+              ++a_cnt[a];
+              a_hi = act_addr + a * kChunkBytes; a_lo = act_addr + (4 + a) * kChunkBytes;
+            }
+            tc_fence_after();
+            for (int nh = 0; nh < nh_cnt; ++nh)
+              chain_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256 + nh * 128), idesc,
+                                kbi == 0, p.passes, nh_cnt == 1 ? issuer == 0 : nh == issuer, tr);
+          }
+          if (elect_one()) umma_commit(&cs.d_full[buf]);            // this warp's share of layer l's accumulator complete
+          __syncwarp();
+        }
+      }
+      if (lane == 0 && issuer == 0) trace_end(tr, 1);
+    }
+  } else if (kTmemA && warp == 2 + kEpiWarps + kIssuers - 1) {
+    // ============================== tape store warp ==============================
+    // streams the bf16 tape images of layers 0..7 out of the three rotating staging slots (one 16 KB block each)
+    if (p.save) {
+      uint8_t* stg = smem + kOffStgT;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        for (int l = 0; l < 8; ++l) {
+          const int t_img = l == 7 ? T_FEAT : T_H0 + l;
+          for (int jp = 0; jp < 8; ++jp) {                         // (block j, part)
+            const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + (uint32_t)jp;
+            const uint32_t slot = qs % 3u, k = qs / 3u;
+            mbar_wait(&cs.g_ready[slot], k & 1);
+            if (elect_one()) {
+              bulk_s2g(p.img.at(t_img, tile, jp >> 1, jp & 1), stg + (size_t)slot * kChunkBytes, kChunkBytes);
+              bulk_commit_group();
+              bulk_wait_read_all();
+              mbar_arrive(&cs.s_free[slot]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (elect_one()) bulk_wait_all();
+      __syncwarp();
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ============================== epilogue warps ==============================
+    const int e = warp - 2;
+    const int q = warp & 3;           // TMEM lane quadrant this warp may access
+    const int cq = e >> 2;            // which 16-column quarter of every 64-column block
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    uint32_t d_cnt[2] = {0, 0};
+    uint8_t* act_hi = smem + kOffAct;
+    uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
+    const float* wts = s_misc + 8;
+    Trace tr; trace_begin(tr);
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
+      const bool tile_ok = tile < p.num_tiles;                       // false only for the dummy half of an odd pair
+      const long long m = (long long)tile * kTileM + row;
+      const bool valid = tile_ok && m < p.M;
+      const long long ray = valid ? m / p.S : 0;
+      const bool save = p.save && tile_ok;
+
+      // ---------------- positional encoding -> A_enc (internal column order: x y z 0 | (sin,cos) pairs)
+      {
+        float x[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          float tv = p.t[m];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) x[c] = add_rn(p.origins[ray * 3 + c], mul_rn(p.dirs[ray * 3 + c], tv));
+        }
+        float vals[16];
+        if (cq == 0) { vals[0] = x[0]; vals[1] = x[1]; vals[2] = x[2]; vals[3] = 0.f; }
+        const int p0 = cq == 0 ? 0 : 8 * cq - 2, np = cq == 0 ? 6 : 8, v0 = cq == 0 ? 4 : 0;   // 6 + 8 + 8 + 8 pairs
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i < np) {
+            int pr = p0 + i;
+            int c = pr / kL, j = pr - c * kL;
+            float arg = mul_rn(c == 0 ? x[0] : (c == 1 ? x[1] : x[2]), band_freq(j));
+            float sn, cs_;
+            sincosf(arg, &sn, &cs_);
+            float w = wts[j];
+            vals[v0 + 2 * i] = mul_rn(sn, w);
+            vals[v0 + 2 * i + 1] = mul_rn(cs_, w);
+          }
+        }
+        Split16 sp;
+        split16<kF16>(vals, sp);
+        store16(sp, row, cq * kEpiCols, enc_blk, enc_blk + kChunkBytes);
+        if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) chain_arrive<kPair>(&cs.a_ready[4], rank);
+        if (save) {
+          if (kF16) split16<false>(vals, sp);
+          store16_image(sp, row, cq * kEpiCols, p.img.at(T_ENC, tile, 0, 0), p.img.at(T_ENC, tile, 0, 1));
+        }
+      }
+
+      // ---------------- layers
+      for (int l = 0; l < kNumLayers; ++l) {
+        const int buf = kTmemA ? 0 : (l & 1);
+        twait(tr, 0, &cs.d_full[buf], d_cnt[buf] & 1);
+        ++d_cnt[buf];
+        tc_fence_after();
+        const int nchunk = l == 8 ? 2 : 4;
+        float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;   // density row (l == 6) or rgb rows (l == 8)
+        uint32_t mbits[2] = {0u, 0u};               // ReLU mask of this thread's 16 columns in each block
+        uint32_t vn[16];                            // accumulator columns of the NEXT block, loaded one block ahead
+        uint32_t va[kTmemA ? 4 : 1][16];            // kTmemA: this thread's whole share of the accumulator
+        if (kTmemA) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nchunk) tmem_ld16(tmem_base + t_lane + (uint32_t)(j * 64 + cq * kEpiCols), va[j]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cs.d_empty[0]);   // the (single) accumulator is free for the next layer's MMAs
+        } else {
+          tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j >= nchunk) break;
+          uint32_t v[16];
+          const int col0 = j * 64 + cq * kEpiCols;
+          if (kTmemA) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = va[j][i];
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = vn[i];
+            if (j + 1 < nchunk) tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + col0 + 64), vn);
+          }
+          float f[16];
+          if (l < 8) {
+            const float* b = s_bias + l * 256 + col0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + b[i], 0.f);
+          } else {
+            const float* b = p.raybias + (size_t)ray * kHW + col0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 bb = *reinterpret_cast<const float4*>(b + i);
+              f[i] = fmaxf(__uint_as_float(v[i]) + bb.x, 0.f);
+              f[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + bb.y, 0.f);
+              f[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + bb.z, 0.f);
+              f[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + bb.w, 0.f);
+            }
+          }
+          if (l == 6) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dot0 = fmaf(f[i], s_w7r0[col0 + i], dot0);
+          }
+          if (save) {
+            uint32_t m16 = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m16 |= (f[i] > 0.f ? 1u : 0u) << i;
+            mbits[j >> 1] |= m16 << (16 * (j & 1));
+          }
+          Split16 sp;
+          if (l == 8) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              dot0 = fmaf(f[i], s_w9[col0 + i], dot0);
+              dot1 = fmaf(f[i], s_w9[128 + col0 + i], dot1);
+              dot2 = fmaf(f[i], s_w9[256 + col0 + i], dot2);
+            }
+            if (save) {   // hid image for the 128->3 head's weight gradient and its ReLU mask
+              split16<false>(f, sp);
+              store16_image(sp, row, cq * kEpiCols, p.img.at(T_HID, tile, j, 0), p.img.at(T_HID, tile, j, 1));
+            }
+          } else if (kTmemA) {
+            split16<kF16>(f, sp);
+            tmem_st8(tmem_base + t_lane + 256u + (uint32_t)(j * 32 + cq * 8), sp.hi);
+            tmem_st8(tmem_base + t_lane + 384u + (uint32_t)(j * 32 + cq * 8), sp.lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+            if (save) {          // bf16 tape image through the staging slots (the store warp bulk-copies them out)
+              if (kF16) split16<false>(f, sp);
+              uint8_t* stg = smem + kOffStgT;
+#pragma unroll
+              for (int part = 0; part < 2; ++part) {
+                const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + 2u * (uint32_t)j + (uint32_t)part;
+                const uint32_t slot = qs % 3u, k = qs / 3u;
+                if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
+                store16_part(part == 0 ? sp.hi : sp.lo, row, cq * kEpiCols, stg + (size_t)slot * kChunkBytes);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
+              }
+            }
+          } else {
+            split16<kF16>(f, sp);
+            store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
+            if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
+            if (save) {
+              const int tsave = l == 7 ? T_FEAT : T_H0 + l;
+              if (kF16) split16<false>(f, sp);
+              store16_image(sp, row, cq * kEpiCols, p.img.at(tsave, tile, j, 0), p.img.at(tsave, tile, j, 1));
+            }
+          }
+        }
+        // accumulator drained: hand it back to the MMA warp (kTmemA did so right after loading it)
+        if (!kTmemA) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
+        }
+        if (save) *p.img.mask_at(tile, l, row, cq) = make_uint2(mbits[0], mbits[1]);
+
+        if (l == 6 || l == 8) {
+          // combine the four column quarters of each row (warps q, q+4, q+8, q+12) through shared memory
+          if (cq != 0) {
+            float* pr = s_part + ((size_t)(cq - 1) * 128 + row) * 4;
+            pr[0] = dot0; pr[1] = dot1; pr[2] = dot2;
+          }
+          named_bar_sync(1, kEpiWarps * 32);
+          if (cq == 0 && valid) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const float* o = s_part + ((size_t)k * 128 + row) * 4;
+              dot0 += o[0]; dot1 += o[1]; dot2 += o[2];
+            }
+            if (l == 6) {
+              float raw = dot0 + s_misc[0];
+              float z = p.noise ? add_rn(raw, p.noise[m]) : raw;
+              p.sigma[m] = softplus_f(z);
+            } else {
+              p.rgb[m * 3 + 0] = sigmoid_f(dot0 + s_misc[1]);
+              p.rgb[m * 3 + 1] = sigmoid_f(dot1 + s_misc[2]);
+              p.rgb[m * 3 + 2] = sigmoid_f(dot2 + s_misc[3]);
+            }
+          }
+          named_bar_sync(1, kEpiWarps * 32);
+        }
+      }
+    }
+    if (lane == 0 && (e == 0 || e == kEpiWarps - 1)) trace_end(tr, e == 0 ? 2 : 3);
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (kPair) cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still signal it
+  if (warp == 1) {
+    if (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1788,6 +1938,7 @@ static void fill_pack_params(const SparfMLP* mlp, PackParams& pp, uint8_t* dst) 
   for (int l = 0; l < 8; ++l) pp.w[l] = mlp->trunk_w[l];
   pp.w[8] = mlp->head_w[0];
   pp.packed = dst;
+  pp.order = 0;
 }
 
 static int weight_copies() {
@@ -1802,7 +1953,8 @@ static int weight_copies() {
 // CTA-pair (cta_group::2) variants of the chain kernels.  Measured on the bench shape (profiles/r01_notes.md): the
 // inference forward is ~11% faster as pairs (half the weight bytes and operand-fetch bandwidth per SM), the taped
 // forward and the dgrad chain are slower (every epilogue hand-off becomes a cluster-scope arrive on the leader).
-// Default: pairs for the inference forward only; SPARF_TC_PAIRS=0 / 1 forces them off / on everywhere.
+// They now only serve the shapes the tensor-memory-operand kernel does not (single-pass engine, bf16 recompute);
+// SPARF_TC_PAIRS=0 / 1 forces them off / on everywhere.
 static int cta_pairs_mode() {
   static int v = -2;
   if (v == -2) {
@@ -1814,6 +1966,16 @@ static int cta_pairs_mode() {
 static bool use_cta_pairs(bool inference) {
   const int m = cta_pairs_mode();
   return m < 0 ? inference : m == 1;
+}
+
+// which forward kernel serves a call: 0 = stand-alone CTAs with shared-memory operands, 1 = CTA pairs,
+// 2 = stand-alone CTAs with the A operand in tensor memory (fp16 3-pass only; SPARF_TC_TMEMA=0 disables it)
+enum { FWD_SMEM = 0, FWD_PAIRS = 1, FWD_TMEM = 2 };
+static int fwd_variant(bool f16, int passes, bool save, int num_tiles) {
+  static const bool tmem_ok = !(getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '0');
+  if (tmem_ok && f16 && passes == 3 && cta_pairs_mode() != 1) return FWD_TMEM;   // 317 us inference / 425 us taped
+  if (use_cta_pairs(!save) && num_tiles >= 2) return FWD_PAIRS;
+  return FWD_SMEM;
 }
 
 #ifdef SPARF_TC_TRACE
@@ -1896,7 +2058,16 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_encgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgSmem + 1024));
     attr_set = true;
   }
-  if (use_cta_pairs(!p.save) && p.num_tiles >= 2) {
+  const int variant = fwd_variant(f16, passes, p.save != 0, p.num_tiles);
+  if (variant == FWD_TMEM) {
+    static bool attr_t = false;
+    if (!attr_t) {
+      SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+      attr_t = true;
+    }
+    tc_mlp_fwd_kernel<true, false, true><<<std::min(p.num_tiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(p);
+    TRACE_DUMP(p.save ? "forward (tape, A in TMEM)" : "forward f16 (A in TMEM)");
+  } else if (variant == FWD_PAIRS) {
     const int pairs = (p.num_tiles + 1) / 2;
     const int grid = 2 * std::min(pairs, num_sms() / 2);
     rc_launch = f16 ? launch_clustered(tc_mlp_fwd_kernel<true, true>, grid, kThreads, kSmemBytes + 1024, st, p)
@@ -1932,6 +2103,8 @@ int tc_mlp_forward(const SparfMLP* mlp, int engine, int R, int S, const float* o
   float* raybias = reinterpret_cast<float*>(packed + align_up((size_t)16 * kChunksPerTile * kChunkBytes, 256));
   PackParams pp;
   fill_pack_params(mlp, pp, packed);
+  const int passes_ = engine == SPARF_ENGINE_TC_1X ? 1 : 3;
+  pp.order = fwd_variant(true, passes_, false, (int)(((long long)R * S + kTileM - 1) / kTileM)) == FWD_TMEM ? 1 : 0;
   pack_weights_kernel<true><<<dim3(kChunksPerTile, weight_copies()), 256, 0, st>>>(pp);
   SPARF_CHECK_LAUNCH("pack_weights_kernel");
   C2F c2f{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
@@ -1963,6 +2136,7 @@ int tc_mlp_forward_tape(const SparfMLP* mlp, int engine, int R, int S, const flo
   float* denc = reinterpret_cast<float*>(tp + align_up(fwd_images_bytes(ntiles), 1024));
   PackParams pp;
   fill_pack_params(mlp, pp, packed);
+  pp.order = fwd_variant(true, 3, true, ntiles) == FWD_TMEM ? 1 : 0;
   pack_weights_kernel<true><<<kChunksPerTile, 256, 0, st>>>(pp);
   SPARF_CHECK_LAUNCH("pack_weights_kernel");
   C2F c2f{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
