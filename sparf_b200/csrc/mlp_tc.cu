@@ -182,18 +182,29 @@ __global__ void pack_weights_kernel(PackParams pp) {
   const int ldw = l == 0 ? 63 : (l == 4 ? 319 : (l == 8 ? 283 : 256));
   const float* W = pp.w[l];
   uint8_t* dst = pp.packed + (size_t)chunk * kChunkBytes;
-  for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
-    int n = e >> 6, k = e & 63;
-    int row = (l == 7 ? 1 : 0) + nh * 128 + n;
-    int col;
-    if (enc) {
-      int rc = enc_ref_col(k);
-      col = rc < 0 ? -1 : (l == 0 ? 0 : kW) + rc;
-    } else {
-      col = kb_act_index(l, kbi) * 64 + k;
+  // one thread = 8 consecutive K elements of one output row = one 16-byte store into the swizzled image
+  for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
+    const int n = e >> 3, k0 = (e & 7) * 8;
+    const int row = (l == 7 ? 1 : 0) + nh * 128 + n;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = k0 + 2 * i + h;
+        int col;
+        if (enc) {
+          const int rc = enc_ref_col(k);
+          col = rc < 0 ? -1 : (l == 0 ? 0 : kW) + rc;
+        } else {
+          col = kb_act_index(l, kbi) * 64 + k;
+        }
+        v[h] = col < 0 ? 0.f : __ldg(W + (size_t)row * ldw + col);
+      }
+      w[i] = (uint32_t)split1<kF16>(v[0], part) | ((uint32_t)split1<kF16>(v[1], part) << 16);
     }
-    float v = col < 0 ? 0.f : W[(size_t)row * ldw + col];
-    *reinterpret_cast<uint16_t*>(dst + sw128_offset(n, k)) = split1<kF16>(v, part);
+    *reinterpret_cast<uint4*>(dst + sw128_offset(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -214,12 +225,19 @@ __global__ void pack_weights_bwd_kernel(PackParams pp) {
   const int rowoff = l == 7 ? 1 : 0;
   const float* W = pp.w[l];
   uint8_t* dst = pp.packed + (size_t)chunk * kChunkBytes;
-  for (int e = threadIdx.x; e < 128 * 64; e += blockDim.x) {
-    int n = e >> 6, k = e & 63;
-    int in_idx = nh * 128 + n;         // column of W (input feature of the forward layer)
-    int out_idx = kbi * 64 + k;        // row of W (output feature)
-    float v = W[(size_t)(rowoff + out_idx) * ldw + in_idx];
-    *reinterpret_cast<uint16_t*>(dst + sw128_offset(n, k)) = split1<false>(v, part);
+  // thread = (8 K elements, one row n), n fastest across the threads: the transposed reads W[out][in = n] coalesce
+  for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
+    const int n = e & 127, k0 = (e >> 7) * 8;
+    const int in_idx = nh * 128 + n;         // column of W (input feature of the forward layer)
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int out_idx = kbi * 64 + k0 + 2 * i;   // row of W (output feature)
+      const float v0 = __ldg(W + (size_t)(rowoff + out_idx) * ldw + in_idx);
+      const float v1 = __ldg(W + (size_t)(rowoff + out_idx + 1) * ldw + in_idx);
+      w[i] = (uint32_t)split1<false>(v0, part) | ((uint32_t)split1<false>(v1, part) << 16);
+    }
+    *reinterpret_cast<uint4*>(dst + sw128_offset(n, k0)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -1636,13 +1654,31 @@ __global__ void __launch_bounds__(256) image_reduce_kernel(const __grid_constant
   }
 }
 
-// per-ray sum of g_hid over the samples: rayS[r][n] = sum_k GHID[(r,k)][n]
-__global__ void ray_sum_ghid_kernel(Images img, int R, int S, float* __restrict__ rayS) {
-  const int n = threadIdx.x;        // 128
-  const int r = blockIdx.x;
-  float acc = 0.f;
-  for (int k = 0; k < S; ++k) acc += img_value(img, T_GHID, (long long)r * S + k, n);
-  rayS[(size_t)r * kHW + n] = acc;
+// per-ray sum of g_hid over the samples: rayS[r][n] = sum_k GHID[(r,k)][n].  Block = one ray, 128 threads =
+// 8 sample groups x 16 sixteen-byte chunks (8 features each), reduced through shared memory.
+__global__ void __launch_bounds__(128) ray_sum_ghid_kernel(Images img, int R, int S, float* __restrict__ rayS) {
+  __shared__ float red[8][128];
+  const int r = blockIdx.x, c = threadIdx.x & 15, g = threadIdx.x >> 4;   // chunk c: features 8c..8c+7
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int k = g; k < S; k += 8) {
+    const long long m = (long long)r * S + k;
+    const int tile = (int)(m >> 7), row = (int)(m & 127);
+    const uint32_t off = sw128_offset(row, (c & 7) * 8);
+    float x[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(img.at(T_GHID, tile, c >> 3, 0) + off)),
+            __ldg(reinterpret_cast<const uint4*>(img.at(T_GHID, tile, c >> 3, 1) + off)), x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += x[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[g][c * 8 + i] = acc[i];
+  __syncthreads();
+  float v = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v += red[q][threadIdx.x];
+  rayS[(size_t)r * kHW + threadIdx.x] = v;
 }
 
 // view-direction part of the colour head: dW8[n][256+k] += sum_r rayS[r][n] denc[r][k]
