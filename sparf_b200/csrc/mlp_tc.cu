@@ -1575,6 +1575,7 @@ struct ReduceJob {
 
 struct ReduceJobs { ReduceJob j[16]; };
 
+template <int NC>   // NC = 0 (column sums) | 1 | 3 narrow outputs: sizes the accumulators (registers -> blocks per SM)
 __global__ void __launch_bounds__(256) image_reduce_kernel(const __grid_constant__ ReduceJobs jobs, Images img, long long M,
                                                            int ntiles, int tiles_per_block) {
   __shared__ float red[8][32][25];
@@ -1582,10 +1583,11 @@ __global__ void __launch_bounds__(256) image_reduce_kernel(const __grid_constant
   const int tid = threadIdx.x, c16 = tid & 31, rg = tid >> 5;
   const int fb = c16 >> 3, c = c16 & 7;
   const bool active = fb < job.nblk;
-  const int nc = job.nc;
-  float acc[24];
+  constexpr int nc = NC;
+  constexpr int kAcc = NC == 0 ? 8 : NC * 8;
+  float acc[kAcc];
 #pragma unroll
-  for (int i = 0; i < 24; ++i) acc[i] = 0.f;
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
   float accb[3] = {0.f, 0.f, 0.f};
   const int t0 = blockIdx.x * tiles_per_block, t1 = min(ntiles, t0 + tiles_per_block);
   for (int tile = t0; tile < t1; ++tile) {
@@ -2329,8 +2331,14 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     add_red(T_H0 + 6, 4, 1, c.g_raw, 1, grad->trunk_w[7], kW, grad->trunk_b[7]);        // density row of trunk 7
     add_red(T_HID, 2, 3, c.g_pre, 4, grad->head_w[1], kHW, grad->head_b[1]);             // 128 -> 3 colour layer
     const int tpb = 4;
-    image_reduce_kernel<<<dim3(ceil_div(ntiles, tpb), nrj), 256, 0, st>>>(rj_tab, img, Mc, ntiles, tpb);
-    SPARF_CHECK_LAUNCH("image_reduce_kernel");
+    // one launch per job shape (blockIdx.y = job index is passed through the first table entry of each launch)
+    ReduceJobs one;
+    one.j[0] = rj[0];
+    image_reduce_kernel<1><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, st>>>(one, img, Mc, ntiles, tpb);
+    SPARF_CHECK_LAUNCH("image_reduce_kernel<1>");
+    one.j[0] = rj[1];
+    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, st>>>(one, img, Mc, ntiles, tpb);
+    SPARF_CHECK_LAUNCH("image_reduce_kernel<3>");
     ray_sum_ghid_kernel<<<nr, 128, 0, st>>>(img, nr, S, c.rayS);
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
     ray_head_wgrad_kernel<<<ceil_div(nr, 8), 128, 0, st>>>(nr, 8, c.rayS, c.denc, grad->head_w[0]);
