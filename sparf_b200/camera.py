@@ -6,6 +6,7 @@ it is a handful of 3x4 matrices per step and receives dL/d(pose_w2c) from the ra
 """
 from __future__ import annotations
 
+import math
 from typing import List, Tuple
 
 import torch
@@ -93,9 +94,77 @@ class Lie:
         V = I + B * wx + C * wx @ wx
         return torch.cat([R, V @ u[..., None]], dim=-1)
 
+    def SO3_to_so3(self, R, eps=1e-7):
+        """Rotation matrix -> axis-angle vector (camera.py:133-140): theta from the clamped trace (taken modulo pi, the
+        reference's guard against theta == pi), w = vee((R - R^T) / (2 sin(theta)/theta))."""
+        trace = R[..., 0, 0] + R[..., 1, 1] + R[..., 2, 2]
+        theta = torch.remainder(torch.acos(((trace - 1) / 2).clamp(-1 + eps, 1 - eps)), math.pi)[..., None, None]
+        lnR = 1 / (2 * self.taylor_A(theta) + 1e-8) * (R - R.transpose(-2, -1))
+        return torch.stack([lnR[..., 2, 1], lnR[..., 0, 2], lnR[..., 1, 0]], dim=-1)
+
+    def SE3_to_se3(self, Rt, eps=1e-8):
+        """[R|t] -> (w, u) with t = V(w) u (camera.py:159-170)."""
+        R, t = Rt.split([3, 1], dim=-1)
+        w = self.SO3_to_so3(R)
+        wx = self.skew_symmetric(w)
+        theta = w.norm(dim=-1)[..., None, None]
+        I = torch.eye(3, device=w.device, dtype=torch.float32)
+        A, B = self.taylor_A(theta), self.taylor_B(theta)
+        invV = I - 0.5 * wx + (1 - A / (2 * B)) / (theta ** 2 + eps) * wx @ wx
+        return torch.cat([w, (invV @ t)[..., 0]], dim=-1)
+
+
+class Quaternion:
+    """Unit-quaternion pose parametrisation, scalar first (camera.py:207-291)."""
+
+    def q_to_R(self, q):
+        qa, qb, qc, qd = torch.nn.functional.normalize(q, dim=-1).unbind(dim=-1)
+        rows = [[1 - 2 * (qc ** 2 + qd ** 2), 2 * (qb * qc - qa * qd), 2 * (qa * qc + qb * qd)],
+                [2 * (qb * qc + qa * qd), 1 - 2 * (qb ** 2 + qd ** 2), 2 * (qc * qd - qa * qb)],
+                [2 * (qb * qd - qa * qc), 2 * (qa * qb + qc * qd), 1 - 2 * (qb ** 2 + qc ** 2)]]
+        return torch.stack([torch.stack(r, dim=-1) for r in rows], dim=-2)
+
+    def R_to_q(self, R, eps=1e-8):
+        """Batched [B,3,3] rotations -> quaternions with w >= 0 via the dominant eigenvector of the symmetric 4x4
+        matrix built from R (host-side numpy, not differentiable, like the reference: camera.py:242-275)."""
+        import numpy as np
+        dev = R.device if torch.is_tensor(R) else None
+        Rn = R.detach().cpu().numpy() if torch.is_tensor(R) else np.asarray(R)
+        assert Rn.ndim == 3, "R_to_q expects a batch of rotation matrices"
+        out = []
+        for M in Rn:
+            (xx, yx, zx), (xy, yy, zy), (xz, yz, zz) = M        # row-major unpack, i.e. R.flat order
+            K = np.array([[xx - yy - zz, 0, 0, 0],
+                          [yx + xy, yy - xx - zz, 0, 0],
+                          [zx + xz, zy + yz, zz - xx - yy, 0],
+                          [yz - zy, zx - xz, xy - yx, xx + yy + zz]]) / 3.0
+            vals, vecs = np.linalg.eigh(K)
+            q = vecs[[3, 0, 1, 2], np.argmax(vals)]
+            out.append(-q if q[0] < 0 else q)
+        q = np.stack(out, axis=0)
+        return torch.from_numpy(q).to(dev).float() if dev is not None else q
+
+    def invert(self, q):
+        qa, qb, qc, qd = q.unbind(dim=-1)
+        return torch.stack([qa, -qb, -qc, -qd], dim=-1) / q.norm(dim=-1, keepdim=True) ** 2
+
+    def product(self, q1, q2):
+        a1, b1, c1, d1 = q1.unbind(dim=-1)
+        a2, b2, c2, d2 = q2.unbind(dim=-1)
+        return torch.stack([a1 * a2 - b1 * b2 - c1 * c2 - d1 * d2,
+                            a1 * b2 + b1 * a2 + c1 * d2 - d1 * c2,
+                            a1 * c2 - b1 * d2 + c1 * a2 + d1 * b2,
+                            a1 * d2 + b1 * c2 - c1 * b2 + d1 * a2], dim=-1)
+
+
+def to_hom(X):
+    """Homogeneous coordinates (camera.py:297-300)."""
+    return torch.cat([X, torch.ones_like(X[..., :1])], dim=-1)
+
 
 pose = Pose()
 lie = Lie()
+quaternion = Quaternion()
 
 
 def get_center_and_ray(pose_w2c: torch.Tensor, H: int, W: int, intr: torch.Tensor, ray_idx=None
