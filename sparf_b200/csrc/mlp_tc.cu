@@ -1,25 +1,30 @@
 // tcgen05 engine for the NeRF MLP (SPARF_ENGINE_TC_3X / TC_1X), sm_100a.
 //
-// FORWARD  (tc_mlp_fwd_kernel): one persistent, warp-specialised kernel.  A CTA owns 128 sample rows at a
-// time (one TMEM lane per row) and pushes them through all 9 tensor-core layers without the activations
-// leaving the SM:
-//   warp 0      weight producer : streams pre-packed 16-bit (hi | lo) weight blocks, 16 KB each, from L2 into a
-//                                 3-deep shared-memory ring with cp.async.bulk + mbarrier complete_tx
-//   warp 1      MMA issuer      : one thread issues tcgen05.mma (M=128, N=128, K=16) into one of TWO 256-column
-//                                 fp32 TMEM accumulators (ping-pong per layer), commits to mbarriers
-//   warps 2-9   epilogue        : positional encoding -> A operand; per layer TMEM -> registers -> bias/ReLU ->
-//                                 (hi, lo) split -> next layer's A operand in shared memory, handed to the MMA
-//                                 warp per 64-column K block so layer l+1 starts while layer l drains; density
-//                                 row, colour head (128->3) and activations in fp32 on CUDA cores
+// CHAIN KERNELS (tc_mlp_fwd_kernel, tc_mlp_dgrad_kernel): persistent, warp-specialised, one CTA per SM.  A CTA owns
+// 128 sample rows at a time (one TMEM lane per row) and pushes them through all tensor-core layers without the
+// activations leaving the SM.  Default variant (kTmemA): the A operand of every layer lives in TENSOR
+// MEMORY -- TMEM = one 256-column fp32 accumulator | A hi | A lo --
+//   warp 0      weight producer : streams pre-packed 16-bit (hi | lo) weight chunks, 16 KB each, from L2 into an
+//                                 8..10-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx
+//   warp 1      MMA issuer      : an elected lane issues tcgen05.mma M128 x N256 x K16 (A from TMEM, B = two adjacent
+//                                 ring stages; the encoder block's A from shared memory), commits to mbarriers
+//   warps 2-17  epilogue        : positional encoding (forward); per layer: whole accumulator share -> registers,
+//                                 accumulator handed back, then per 64-column block bias/ReLU or mask -> (hi, lo) split
+//                                 -> tcgen05.st -> the MMA warp starts the next layer on that K block; density row,
+//                                 colour head (128 -> 3) and activations in fp32 on CUDA cores
+//   warp 19     image store     : bulk-copies the staged bf16 tape / gradient images from shared memory to HBM
+// Older variants stay for the shapes the TMEM kernels do not cover and for comparison: operands in shared memory with
+// two N128 issuer warps (warps 1 and 18), and CTA pairs (cta_group::2, kPair).
 //
-// BACKWARD (tc_mlp_backward): nothing is kept from the forward call; per row chunk
-//   1. the forward kernel re-runs in bf16 "save" mode and dumps every layer's A-operand image to HBM,
-//   2. tc_mlp_dgrad_kernel (same skeleton, transposed weights) chains dL/dz_l from the colour head down to
-//      layer 0, ReLU masks read from the saved images, and dumps each dL/dz_l image,
-//   3. tc_mlp_wgrad_kernel computes dW_l = (dL/dz_l)^T x_l over the row chunk: the saved images are consumed
-//      AS THEY ARE through MN-major descriptors (reduction over rows), fp32 accumulation in TMEM, one
-//      atomic flush per CTA,
-//   4. small CUDA-core kernels finish biases, the density row, the 128->3 head and the view-direction part.
+// BACKWARD (tc_mlp_backward_tape; tc_mlp_backward re-runs the forward in bf16 "save" mode first):
+//   1. the taped forward dumped every layer's A-operand image (bf16 hi | lo) and 64-bit ReLU masks,
+//   2. tc_mlp_dgrad_kernel (transposed weights) chains dL/dz_l from the colour head down to layer 0 and dumps each
+//      dL/dz_l image,
+//   3. tc_mlp_wgrad_kernel computes dW_l = (dL/dz_l)^T x_l: the saved images are consumed AS THEY ARE through MN-major
+//      descriptors (reduction over rows), fp32 accumulation in TMEM, one atomic flush per CTA; its reducer warps sum
+//      the gradient blocks over rows (bias gradients),
+//   4. small CUDA-core kernels finish the density row, the 128 -> 3 head and the view-direction part,
+//   5. tc_mlp_encgrad_kernel (pose optimisation): dL/d(encoding) on tensor cores, encoding backward + per-ray sums.
 //
 // PRECISION: x*W = x_hi*W_hi + x_lo*W_hi + x_hi*W_lo with 16-bit operand halves and fp32 accumulation
 // (SURVEY.md hard part 1).  Forward halves are fp16 (2^-22 relative: fp32-like), backward halves are bf16
@@ -48,9 +53,9 @@ constexpr int kEv = 27;
 constexpr int kNumLayers = 9;    // forward tensor-core layers: trunk 0..7 + head 0
 constexpr int kNumBwdLayers = 8; // backward tensor-core layers
 constexpr int kTileM = 128;
-constexpr int kStages = 3;         // weight-ring stages of the forward kernel
-constexpr int kBwdStages = 6;      // ... of the dgrad kernel: its ring takes everything between the activations and the
-                                   // barriers (encoder blocks, forward ring, bias / small-weight tables it does not use)
+constexpr int kStages = 3;         // weight-ring stages of the shared-memory-operand forward kernel
+constexpr int kBwdStages = 6;      // ... of the shared-memory-operand dgrad kernel (its ring takes the encoder blocks, the
+                                   // forward ring and the bias / small-weight tables it does not use)
 constexpr int kMaxStages = 10;
 constexpr int kChunkBytes = 16384;  // one [128 x 64] 16-bit operand block
 constexpr int kEpiWarps = 16;       // 4 TMEM lane quadrants x 4 column quarters of every 64-column block
