@@ -248,7 +248,7 @@ def run_ours(args):
                     traffic=4.752e9 if args.engine in ("auto", "tc_3x") else None,
                     traffic_source="profiles/r01_ncu_chain.md (ncu --set full, per step)",
                     engine=args.engine)
-    cpu = cpu_baseline(sample_steps=2)
+    cpu = cpu_baseline(sample_steps=2) if world == 1 else None   # reported on rank 0 at N = 1 only
     line = dict(metric="rays/sec (fwd+bwd, 128 samples/ray)", value=value, unit="rays/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32 in/out; GEMMs: " + args.engine, data="synthetic",
