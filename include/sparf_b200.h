@@ -104,10 +104,13 @@ int sparf_engine_available(int engine);
 int sparf_raygen_forward(int32_t B, int32_t n, int32_t W, const float* pose_w2c, const float* intr_inv,
                          const int64_t* ray_idx, const float* pixels, int32_t per_image,
                          float* origins, float* dirs, sparf_stream_t stream);
-/* d(origins), d(dirs) [B*n,3] -> d(pose_w2c) [B,3,4], accumulated (+=). */
+/* d(origins), d(dirs) [B*n,3] -> d(pose_w2c) [B,3,4], accumulated (+=).  d_pixels (optional, float-pixel path only):
+ * gradient w.r.t. the pixel locations, same shape as `pixels` -- written for per-image pixels [B,n,2], accumulated (+=,
+ * caller zeroes) for a shared [n,2] list.  The reference's get_center_and_ray_at_pixels is differentiable in the pixels
+ * and the depth-consistency loss relies on it (depth_cons_loss.py:247-283). */
 int sparf_raygen_backward(int32_t B, int32_t n, int32_t W, const float* pose_w2c, const float* intr_inv,
                           const int64_t* ray_idx, const float* pixels, int32_t per_image,
-                          const float* d_origins, const float* d_dirs, float* d_pose_w2c,
+                          const float* d_origins, const float* d_dirs, float* d_pose_w2c, float* d_pixels,
                           sparf_stream_t stream);
 
 /* ---------------------------------------------------------------- depth samples
@@ -129,6 +132,7 @@ int sparf_sample_pdf_merge(int32_t R, int32_t S, int32_t S_fine, float near, flo
  * NeRF.forward_samples (frequency_nerf.py:260-281): x = o + t*d, positional encoding, trunk, softplus
  * density (+ noise[R,S] on the raw value when non-NULL), colour head, sigmoid.
  * Outputs sigma [R,S], rgb [R,S,3].
+ * sparf_mlp_workspace_bytes: `backward` = 0 forward call, 1 sparf_mlp_backward (recompute), 2 sparf_mlp_backward_tape.
  */
 size_t sparf_mlp_workspace_bytes(const SparfMLP* mlp, int32_t R, int32_t S, int32_t backward, int32_t engine);
 int sparf_mlp_forward(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S, const float* origins,
@@ -144,7 +148,8 @@ int sparf_mlp_backward(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S
 /* Tape variants (tcgen05 engine): the TRAINING forward additionally dumps, into a caller-held `tape`, the per-layer
  * operand images the backward needs, so that sparf_mlp_backward_tape skips the recompute.  The tape must stay
  * untouched between the two calls.  sparf_mlp_tape_bytes returns 0 when no tape is available for this call
- * (SIMT engine, unsupported shape, or a batch larger than one backward chunk): use the recompute pair then.
+ * (SIMT engine, unsupported shape, or a tape above 64 GB): use the recompute pair then.  Batches larger than one
+ * backward chunk (1024 row tiles) keep ONE tape and walk it chunk by chunk in the backward.
  * Outputs and numerics of the forward are identical to sparf_mlp_forward. */
 size_t sparf_mlp_tape_bytes(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S);
 int sparf_mlp_forward_tape(const SparfMLP* mlp, int32_t engine, int32_t R, int32_t S, const float* origins,

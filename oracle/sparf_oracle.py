@@ -7,7 +7,7 @@ request), of the algorithm the reference implements in
     source/models/frequency_nerf.py  (positional encoding, 8x256 MLP + colour head, compositing)
     source/utils/camera.py           (pixel -> ray, pose inversion)
     source/models/poses_models/two_columns.py (9-D pose embedding -> [R|t])
-    source/training/core/base_losses.py       (photometric Huber loss)
+    source/training/core/base_losses.py       (photometric Huber loss, DS-NeRF sparse-depth loss)
 
 Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
 `bench.py` may import it; the product (`sparf_b200/`) never does.  Gradients come from torch
@@ -106,6 +106,43 @@ def d9_to_pose(d9: Tensor) -> Tensor:
     b3 = torch.cross(b1, b2, dim=-1)
     R = torch.stack([b1, b2, b3], dim=-2)
     return torch.cat([R, t[..., None]], dim=-1)
+
+
+def _taylor(theta: Tensor, first: int, nth: int = 10) -> Tensor:
+    """sum_i (-1)^i theta^(2i) / d_i, d_i = running product of consecutive integer pairs starting at `first`
+    (camera.py:180-205: A = sin x / x uses pairs (2i)(2i+1) for i > 0; B = (1 - cos x)/x^2 pairs (2i+1)(2i+2);
+    C = (x - sin x)/x^3 pairs (2i+2)(2i+3))."""
+    ans = torch.zeros_like(theta)
+    denom = 1.0
+    for i in range(nth + 1):
+        if first == 0:
+            if i > 0:
+                denom *= (2 * i) * (2 * i + 1)
+        else:
+            denom *= (2 * i + first) * (2 * i + first + 1)
+        ans = ans + (-1) ** i * theta ** (2 * i) / denom
+    return ans
+
+
+def se3_to_SE3(wu: Tensor) -> Tensor:
+    """[...,6] (rotation vector w, translation generator u) -> [...,3,4] = [exp(w^) | V(w) u].   camera.py:142-157."""
+    w, u = wu[..., :3], wu[..., 3:]
+    O = torch.zeros_like(w[..., 0])
+    wx = torch.stack([torch.stack([O, -w[..., 2], w[..., 1]], dim=-1),
+                      torch.stack([w[..., 2], O, -w[..., 0]], dim=-1),
+                      torch.stack([-w[..., 1], w[..., 0], O], dim=-1)], dim=-2)
+    theta = w.norm(dim=-1)[..., None, None]
+    I = torch.eye(3, device=w.device, dtype=wu.dtype)
+    A, B, C = _taylor(theta, 0), _taylor(theta, 1), _taylor(theta, 2)
+    R = I + A * wx + B * wx @ wx
+    V = I + B * wx + C * wx @ wx
+    return torch.cat([R, V @ u[..., None]], dim=-1)
+
+
+def compose_pair(pose_a: Tensor, pose_b: Tensor) -> Tensor:
+    """pose_b o pose_a on [...,3,4].   camera.py:108-115."""
+    Ra, ta, Rb, tb = pose_a[..., :3], pose_a[..., 3:], pose_b[..., :3], pose_b[..., 3:]
+    return torch.cat([Rb @ Ra, Rb @ ta + tb], dim=-1)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -314,6 +351,18 @@ def photometric_loss(out: Dict[str, Tensor], image: Tensor, ray_idx: Tensor) -> 
     if "rgb_fine" in out:
         loss = loss + huber2(out["rgb_fine"].reshape(gt.shape), gt)
     return loss
+
+
+def colmap_depth_loss(depth_maps: Sequence[Dict[str, Tensor]], colmap_depth_at_ray: Sequence[Tensor],
+                      colmap_weight_at_ray: Sequence[Tensor], batch_size: int) -> Tensor:
+    """DS-NeRF sparse-depth term (base_losses.py:385-401): per image with triangulated points,
+    mean(w (d_colmap - d_rendered)^2) for the coarse (+ fine) depth; 0.1 * sum / batch_size."""
+    loss = 0.0
+    for out, d, w in zip(depth_maps, colmap_depth_at_ray, colmap_weight_at_ray):
+        loss = loss + torch.mean(((d - out["depth"].reshape(-1)) ** 2) * w)
+        if "depth_fine" in out:
+            loss = loss + torch.mean(((d - out["depth_fine"].reshape(-1)) ** 2) * w)
+    return 0.1 * loss / batch_size
 
 
 # ----------------------------------------------------------------------------------------------

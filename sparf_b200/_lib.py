@@ -39,7 +39,7 @@ _SIGNATURES = {
     "sparf_launch_count": (ctypes.c_uint64, []),
     "sparf_engine_available": (c_int32, [c_int32]),
     "sparf_raygen_forward": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P]),
-    "sparf_raygen_backward": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P, _P]),
+    "sparf_raygen_backward": (c_int32, [c_int32, c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P]),
     "sparf_sample_depth": (c_int32, [c_int32, c_int32, c_float, c_float, c_int32, _P, _P, _P, _P]),
     "sparf_sample_pdf_merge": (c_int32, [c_int32, c_int32, c_int32, c_float, c_float, _P, _P, _P, _P, _P, _P]),
     "sparf_mlp_workspace_bytes": (c_size_t, [POINTER(SparfMLP), c_int32, c_int32, c_int32, c_int32]),

@@ -20,10 +20,11 @@ void set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int n = 0;
+  static int cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cache[dev & 63];           // per device ordinal (several devices in one process)
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }

@@ -51,7 +51,7 @@ __global__ void raygen_fwd_kernel(int n, const float* __restrict__ pose, const f
 // d(pose_w2c)[b] += sum over the image's rays.  o_c = -sum_j R[j][c] t_j ; d_c = sum_j R[j][c] p_j.
 __global__ void raygen_bwd_kernel(int n, const float* __restrict__ pose, const float* __restrict__ kinv,
                                   PixelSrc src, const float* __restrict__ g_o, const float* __restrict__ g_d,
-                                  float* __restrict__ d_pose) {
+                                  float* __restrict__ d_pose, float* __restrict__ d_pixels) {
   int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   const float* P = pose + b * 12;
   const float* K = kinv + b * 9;
@@ -76,6 +76,26 @@ __global__ void raygen_bwd_kernel(int n, const float* __restrict__ pose, const f
         gt -= go[c] * P[j * 4 + c];
       }
       acc[j * 4 + 3] = gt;
+    }
+    // float pixel locations are differentiable in the reference (camera.py:400-416: ray = R^T K^-1 [u,v,1]): the
+    // depth-consistency loss renders at pixels projected from a rendered depth (depth_cons_loss.py:247-283)
+    if (d_pixels) {
+      float du = 0.f, dv = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          du = fmaf(gd[c] * P[j * 4 + c], K[j * 3 + 0], du);
+          dv = fmaf(gd[c] * P[j * 4 + c], K[j * 3 + 1], dv);
+        }
+      }
+      if (src.per_image) {
+        d_pixels[((size_t)b * n + i) * 2] = du;
+        d_pixels[((size_t)b * n + i) * 2 + 1] = dv;
+      } else {   // one pixel list shared by every image: the gradients of the B images add up
+        atomicAdd(d_pixels + (size_t)i * 2, du);
+        atomicAdd(d_pixels + (size_t)i * 2 + 1, dv);
+      }
     }
   }
   __shared__ float red[12][8];
@@ -404,13 +424,14 @@ extern "C" int sparf_raygen_forward(int32_t B, int32_t n, int32_t W, const float
 extern "C" int sparf_raygen_backward(int32_t B, int32_t n, int32_t W, const float* pose_w2c, const float* intr_inv,
                                      const int64_t* ray_idx, const float* pixels, int32_t per_image,
                                      const float* d_origins, const float* d_dirs, float* d_pose_w2c,
-                                     sparf_stream_t stream) {
+                                     float* d_pixels, sparf_stream_t stream) {
   SPARF_REQUIRE(B > 0 && n >= 0, "raygen: bad sizes B=%d n=%d", B, n);
   SPARF_REQUIRE((ray_idx != nullptr) != (pixels != nullptr), "raygen: exactly one of ray_idx / pixels must be given");
   if (n == 0) return SPARF_OK;
   PixelSrc src{ray_idx, pixels, per_image, W, n};
   dim3 grid(ceil_div(n, 256), B);
-  raygen_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, pose_w2c, intr_inv, src, d_origins, d_dirs, d_pose_w2c);
+  SPARF_REQUIRE(d_pixels == nullptr || pixels != nullptr, "raygen: d_pixels needs the float-pixel path");
+  raygen_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, pose_w2c, intr_inv, src, d_origins, d_dirs, d_pose_w2c, d_pixels);
   SPARF_CHECK_LAUNCH("raygen_bwd_kernel");
   return SPARF_OK;
 }

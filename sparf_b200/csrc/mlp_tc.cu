@@ -1921,8 +1921,14 @@ bool tc_supports(const SparfMLP* mlp) {
 bool tc_backward_available() { return true; }
 static int tape_tiles(int R, int S);
 
-// rays per backward chunk: <= 1024 row tiles of saved images (~2.3 GB)
-static int bwd_chunk_rays(int S) { return std::max(1, (1024 * kTileM) / S); }
+// rays per backward chunk: <= 1024 row tiles of gradient images (~1.1 GB), a whole number of 128-row tiles (a taped
+// forward numbers its tiles over the whole batch, so every chunk has to start on a tile boundary)
+static int gcd_int(int a, int b) { return b == 0 ? a : gcd_int(b, a % b); }
+static int bwd_chunk_rays(int S) {
+  const int unit = kTileM / gcd_int(S, kTileM);          // smallest ray count whose rows fill whole tiles
+  const int n = (1024 * kTileM) / S;
+  return std::max(unit, n - n % unit);
+}
 
 static size_t images_bytes(int ntiles, int t_begin, int t_end) {
   size_t total = 0;
@@ -1931,12 +1937,19 @@ static size_t images_bytes(int ntiles, int t_begin, int t_end) {
 }
 static size_t fwd_images_bytes(int ntiles) { return images_bytes(ntiles, 0, T_GHID) + (size_t)ntiles * kMaskTileBytes; }
 static size_t bwd_images_bytes(int ntiles) { return images_bytes(ntiles, T_GHID, T_COUNT); }
-static void images_assign(Images& img, int ntiles, uint8_t* fwd_base, uint8_t* bwd_base) {
+// Forward tensors: laid out for `ntiles_fwd` tiles, the returned pointers address tile `tile0` of each (a backward chunk
+// of a larger taped batch); gradient tensors: `ntiles_bwd` tiles of the chunk's own workspace.
+static void images_assign(Images& img, int ntiles_fwd, uint8_t* fwd_base, uint8_t* bwd_base, int tile0 = 0, int ntiles_bwd = -1) {
+  if (ntiles_bwd < 0) ntiles_bwd = ntiles_fwd;
   size_t o = 0;
-  for (int t = 0; t < T_GHID; ++t) { img.ptr[t] = fwd_base ? fwd_base + o : nullptr; o += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles; }
-  img.mask = fwd_base ? fwd_base + o : nullptr;
+  for (int t = 0; t < T_GHID; ++t) {
+    const size_t per_tile = (size_t)tensor_nblk(t) * 2 * kChunkBytes;
+    img.ptr[t] = fwd_base ? fwd_base + o + per_tile * tile0 : nullptr;
+    o += per_tile * ntiles_fwd;
+  }
+  img.mask = fwd_base ? fwd_base + o + kMaskTileBytes * tile0 : nullptr;
   o = 0;
-  for (int t = T_GHID; t < T_COUNT; ++t) { img.ptr[t] = bwd_base ? bwd_base + o : nullptr; o += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles; }
+  for (int t = T_GHID; t < T_COUNT; ++t) { img.ptr[t] = bwd_base ? bwd_base + o : nullptr; o += (size_t)tensor_nblk(t) * 2 * kChunkBytes * ntiles_bwd; }
 }
 
 struct BwdCarve {
@@ -1970,9 +1983,9 @@ static BwdCarve bwd_carve(void* ws, int nr, int S, bool with_fwd_images) {
 }
 
 size_t tc_workspace_bytes(const SparfMLP* mlp, int R, int S, int backward, int engine) {
-  if (backward) {
+  if (backward) {   // 1: recompute path (forward images of a chunk live in the workspace); 2: a tape holds them
     int nr = std::min(R, bwd_chunk_rays(S));
-    return bwd_carve(nullptr, nr, S, true).total;
+    return bwd_carve(nullptr, nr, S, backward != 2).total;
   }
   return align_up((size_t)16 * kChunksPerTile * kChunkBytes, 256) + align_up((size_t)R * kHW * sizeof(float), 256) + 256;
 }
@@ -2088,9 +2101,13 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
   cudaError_t rc_launch = cudaSuccess;
   p.save = img != nullptr;
   if (img) p.img = *img; else { for (int i = 0; i < T_COUNT; ++i) p.img.ptr[i] = nullptr; }
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};
+  int dev_ord = 0;
+  cudaGetDevice(&dev_ord);
+  bool& attr_set = attr_set_dev[dev_ord & 63];   // function attributes are per device
   if (!attr_set) {
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
@@ -2103,11 +2120,6 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
   }
   const int variant = fwd_variant(f16, passes, p.save != 0, p.num_tiles);
   if (variant == FWD_TMEM) {
-    static bool attr_t = false;
-    if (!attr_t) {
-      SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
-      attr_t = true;
-    }
     tc_mlp_fwd_kernel<true, false, true><<<std::min(p.num_tiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(p);
     TRACE_DUMP(p.save ? "forward (tape, A in TMEM)" : "forward f16 (A in TMEM)");
   } else if (variant == FWD_PAIRS) {
@@ -2193,9 +2205,11 @@ int tc_mlp_forward_tape(const SparfMLP* mlp, int engine, int R, int S, const flo
 // tape = what the training forward keeps for the backward: the forward operand images of every row tile
 // followed by the per-ray view-direction encoding [R,32]
 static int tape_tiles(int R, int S) { return (int)(((long long)R * S + kTileM - 1) / kTileM); }
+constexpr size_t kMaxTapeBytes = (size_t)64 << 30;   // beyond this the backward recomputes the forward chunk by chunk
 size_t tc_tape_bytes(const SparfMLP* mlp, int R, int S) {
-  if (!tc_supports(mlp) || R > bwd_chunk_rays(S)) return 0;   // larger batches recompute chunk by chunk
-  return align_up(fwd_images_bytes(tape_tiles(R, S)), 1024) + align_up((size_t)R * 32 * 4, 1024);
+  if (!tc_supports(mlp)) return 0;
+  const size_t need = align_up(fwd_images_bytes(tape_tiles(R, S)), 1024) + align_up((size_t)R * 32 * 4, 1024);
+  return need <= kMaxTapeBytes ? need : 0;
 }
 
 static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
@@ -2235,8 +2249,8 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     set_error("tcgen05 engine: unsupported MLP shape");
     return SPARF_ERR_UNSUPPORTED;
   }
-  if (workspace_bytes < tc_workspace_bytes(mlp, R, S, 1, engine)) {
-    set_error("tc_mlp_backward: workspace %zu < %zu bytes", workspace_bytes, tc_workspace_bytes(mlp, R, S, 1, engine));
+  if (workspace_bytes < tc_workspace_bytes(mlp, R, S, tape ? 2 : 1, engine)) {
+    set_error("tc_mlp_backward: workspace %zu < %zu bytes", workspace_bytes, tc_workspace_bytes(mlp, R, S, tape ? 2 : 1, engine));
     return SPARF_ERR_WORKSPACE;
   }
   const int nrc = std::min(R, bwd_chunk_rays(S));
@@ -2248,11 +2262,15 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     const int ntiles = (int)((Mc + kTileM - 1) / kTileM);
     BwdCarve c = bwd_carve(workspace, nr, S, tape == nullptr);
     Images img;
-    images_assign(img, ntiles, tape ? tape : c.images_f, c.images_b);
-    if (tape) {   // single chunk by construction (tc_tape_bytes): forward images + denc come from the tape
-      c.denc = reinterpret_cast<float*>(tape + align_up(fwd_images_bytes(ntiles), 1024));
-      c.sigma = const_cast<float*>(sigma_fwd);
-      c.rgb = const_cast<float*>(rgb_fwd);
+    if (tape) {   // forward images + denc + forward outputs of the whole batch come from the tape; this chunk = tiles
+                  // [m0 / 128, ...) of it (bwd_chunk_rays keeps every chunk on a tile boundary)
+      const int ntiles_all = tape_tiles(R, S);
+      images_assign(img, ntiles_all, tape, c.images_b, (int)(m0 / kTileM), ntiles);
+      c.denc = reinterpret_cast<float*>(tape + align_up(fwd_images_bytes(ntiles_all), 1024)) + (size_t)r0 * 32;
+      c.sigma = const_cast<float*>(sigma_fwd) + m0;
+      c.rgb = const_cast<float*>(rgb_fwd) + m0 * 3;
+    } else {
+      images_assign(img, ntiles, c.images_f, c.images_b);
     }
 
     PackParams pp;

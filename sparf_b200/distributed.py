@@ -33,38 +33,57 @@ def shard_rays(ray_idx: torch.Tensor, rank: Optional[int] = None, world: Optiona
 
 class FlatGradients:
     """Points every parameter's `.grad` at a view of one flat fp32 buffer so that zeroing, the global-norm
-    clip and the all-reduce are single operations.  Works with any optimiser (it only sees `.grad`)."""
+    clip and the all-reduce are single operations.
 
-    def __init__(self, modules: Iterable[torch.nn.Module]):
+    Contract with the optimiser loop: zero gradients with `fg.zero_()` (or `optimizer.zero_grad(set_to_none=False)`),
+    NOT with the default `zero_grad()`, which sets `.grad = None` and thereby detaches the parameters from the flat
+    buffer.  `all_reduce` / `clip_grad_norm_` / `has_nonfinite` verify the aliasing first: a detached `.grad = None` is
+    re-attached, a `.grad` that points at other storage raises (its contents would silently miss the collective).
+    The `progress` scalar of the NeRF modules (written via `.data.fill_`, never differentiated) is left out."""
+
+    def __init__(self, modules: Iterable[torch.nn.Module], skip_names=("progress",)):
         self.params: List[torch.nn.Parameter] = []
         seen = set()
         for m in modules:
-            for p in m.parameters():
-                if p.requires_grad and id(p) not in seen:
+            for name, p in m.named_parameters():
+                if p.requires_grad and id(p) not in seen and name.split(".")[-1] not in skip_names:
                     seen.add(id(p))
                     self.params.append(p)
         dev = self.params[0].device
         self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
+        self._views = []
         o = 0
         for p in self.params:
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            v = self.flat[o:o + p.numel()].view_as(p)
+            self._views.append(v)
+            p.grad = v
+            # this parameter has persistent, contiguous fp32 .grad storage: the MLP backward kernels may accumulate
+            # into it directly (ops.MLPFunction.backward checks the mark on every parameter of the call)
+            p._sparf_inplace_grad = True
             o += p.numel()
-        # every parameter now has persistent, contiguous fp32 .grad storage: let the MLP backward kernels
-        # accumulate into it directly (see ops.ACCUMULATE_INTO_PARAM_GRAD)
-        from . import ops
-        ops.ACCUMULATE_INTO_PARAM_GRAD[0] = True
+
+    def check_attached(self):
+        for p, v in zip(self.params, self._views):
+            if p.grad is None:
+                p.grad = v                      # optimizer.zero_grad(set_to_none=True): re-attach (the view is zeroed by zero_())
+            elif p.grad.data_ptr() != v.data_ptr():
+                raise RuntimeError("FlatGradients: a parameter's .grad no longer aliases the flat buffer (use fg.zero_() "
+                                   "or zero_grad(set_to_none=False)); its gradient would miss the all-reduce")
 
     def zero_(self):
+        self.check_attached()
         self.flat.zero_()
 
     def all_reduce(self, group=None):
         """Sum over ranks (one collective per step).  No-op in a single process."""
+        self.check_attached()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
     def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
         """Global-norm clip on the (already reduced) flat buffer; same semantics as
         torch.nn.utils.clip_grad_norm_ over all parameters (base.py:96-97, iter_based_trainer.py:144-146)."""
+        self.check_attached()
         total = self.flat.norm(2)
         coef = (max_norm / (total + 1e-6)).clamp(max=1.0)
         self.flat.mul_(coef)
@@ -72,6 +91,7 @@ class FlatGradients:
 
     def has_nonfinite(self) -> torch.Tensor:
         """Decision for the NaN/Inf 'skip step' guard, taken on the reduced buffer so ranks agree."""
+        self.check_attached()
         return ~torch.isfinite(self.flat).all()
 
 

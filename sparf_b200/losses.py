@@ -4,6 +4,7 @@
     BasePhotoandReguLoss              base_losses.py:243    photometric Huber / MSE (+ fg-mask)
     CorrespondencesPairRenderDepthAndGet3DPtsAndReproject   corres_loss.py:29 + base_corres_loss.py:28
     DepthConsistencyLoss              depth_cons_loss.py:32
+    SparseCOLMAPDepthLoss             base_losses.py:326    DS-NeRF sparse-depth term
     define_loss                       loss_factory.py:25
 
 Same constructor arguments, `compute_loss(opt, data_dict, output_dict, iteration, mode, plot)` ->
@@ -128,6 +129,11 @@ def _with_defaults(defaults: Dict[str, Any], opt) -> edict:
 class Loss:
     """Runs every loss module and combines them (base_losses.py:26-135)."""
 
+    # The reference asserts every term finite on the host each step (base_losses.py:118-124): one device
+    # synchronisation per loss key.  `check_finite = False` (or a CUDA-graph capture in progress) skips the asserts so
+    # that a step stays sync-free; the fused optimiser's non-finite guard (csrc/optim.cu) then covers the same failure.
+    check_finite = True
+
     def __init__(self, loss_modules):
         self.loss_modules = loss_modules
 
@@ -163,15 +169,16 @@ class Loss:
                 out.update(m.get_flow_metrics())
         return out
 
-    @staticmethod
-    def _checked(opt, loss_dict):
+    def _checked(self, opt, loss_dict):
         assert "all" not in loss_dict
+        check = self.check_finite and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing())
         for key in loss_dict:
             assert key in opt.loss_weight, key
             assert loss_dict[key].shape == ()
             if opt.loss_weight[key] is not None:
-                assert not torch.isinf(loss_dict[key]), "loss {} is Inf".format(key)
-                assert not torch.isnan(loss_dict[key]), "loss {} is NaN".format(key)
+                if check:
+                    assert not torch.isinf(loss_dict[key]), "loss {} is Inf".format(key)
+                    assert not torch.isnan(loss_dict[key]), "loss {} is NaN".format(key)
                 yield key
 
     def summarize_loss_w_equal_weights(self, opt, loss_dict):
@@ -249,9 +256,9 @@ class BasePhotoandReguLoss(BaseLoss):
         self.opt, self.net, self.train_data = opt, nerf_net, train_data
 
     def compute_loss(self, opt, data_dict, output_dict, iteration, mode=None, plot=False, **kwargs):
-        loss_dict = edict(render=torch.tensor(0.0, requires_grad=True).to(self.device))
         if iteration < self.opt.start_iter.photometric:
-            return loss_dict, {}, {}
+            return edict(render=torch.zeros((), device=self.device, requires_grad=True)), {}, {}
+        loss_dict = edict()
         B = len(data_dict.idx)
         image = data_dict.image.reshape(B, 3, -1).permute(0, 2, 1)                       # [B,HW,3]
         fg_mask = data_dict.fg_mask.float().view(B, -1, 1) if opt.loss_weight.fg_mask is not None else None
@@ -544,13 +551,53 @@ class DepthConsistencyLoss(BaseLoss):
         return loss, stats, {}
 
 
+# ------------------------------------------------------------------------------------------------
+# DS-NeRF sparse-depth loss
+# ------------------------------------------------------------------------------------------------
+class SparseCOLMAPDepthLoss(BaseLoss):
+    """Weighted squared error between the rendered depth and sparse COLMAP depth, rendered per image at the pixels
+    that carry a triangulated point (base_losses.py:326-402).  `output_dict` is unused, as in the reference."""
+
+    def __init__(self, opt, nerf_net, device):
+        super().__init__(device)
+        self.opt, self.net = opt, nerf_net
+
+    def compute_loss(self, opt, data_dict, output_dict, iteration, mode=None, plot=False, **kwargs):
+        if mode != "train":
+            return {}, {}, {}
+        H, W = data_dict.image.shape[-2:]
+        pose = self.net.get_w2c_pose(opt, data_dict, mode=mode)
+        intr = data_dict.intr
+        depth_maps = data_dict.colmap_depth.view(-1, H, W)
+        conf_maps = data_dict.colmap_conf.view(-1, H, W)
+        B = pose.shape[0]
+        stats = {"perc_col_depth": (depth_maps > 0).sum() / depth_maps.nelement()}
+        per_image = opt.nerf.rand_rays // B
+        total = torch.zeros((), device=self.device)
+        for i in range(B):
+            ys, xs = torch.where(depth_maps[i] > 1e-6)
+            if len(ys) == 0:
+                continue
+            if len(ys) > per_image:
+                sel = torch.randperm(len(ys), device=self.device)[:per_image]
+                ys, xs = ys[sel], xs[sel]
+            d_ref = depth_maps[i][ys, xs].reshape(-1)
+            w_ref = conf_maps[i][ys, xs].reshape(-1)
+            ret = self.net.render_image_at_specific_pose_and_rays(self.opt, data_dict, pose[i], intr[i], H, W,
+                                                                  ray_idx=ys * W + xs, mode="train", iter=iteration)
+            total = total + torch.mean(((d_ref - ret.depth.reshape(-1)) ** 2) * w_ref)
+            if "depth_fine" in ret.keys():
+                total = total + torch.mean(((d_ref - ret.depth_fine.reshape(-1)) ** 2) * w_ref)
+        return edict(colmap_depth=0.1 * total / B), stats, {}      # DS-NeRF's weighting
+
+
 def define_loss(loss_type: str, opt, nerf_net, train_data, device, flow_net=None) -> Loss:
     """loss_factory.py:25-42."""
     mods = []
     if "photometric" in loss_type:
         mods.append(BasePhotoandReguLoss(opt, nerf_net, train_data=train_data, device=device))
     if "SparseCOLMAPDepthLoss" in loss_type:
-        raise NotImplementedError("DS-NeRF sparse-depth loss is a SURVEY §8f row")
+        mods.append(SparseCOLMAPDepthLoss(opt, nerf_net, device=device))
     if "corres" in loss_type:
         mods.append(CorrespondencesPairRenderDepthAndGet3DPtsAndReproject(opt, nerf_net, flow_net=flow_net,
                                                                           train_data=train_data, device=device))

@@ -20,12 +20,15 @@ USE_TAPE = [True]
 # Opt-in: let the MLP backward accumulate straight into existing `param.grad` storage (the C ABI accumulates, +=)
 # instead of returning fresh gradient tensors for autograd to add.  Saves ~20 tiny kernels and a 2 MB memset per
 # render pass.  Only valid for plain `loss.backward()` training loops (no torch.autograd.grad / grad hooks / DDP
-# hooks on these parameters); sparf_b200.distributed.FlatGradients enables it.
+# hooks on these parameters).  Per parameter set: sparf_b200.distributed.FlatGradients marks its parameters
+# (`p._sparf_inplace_grad`); the global switch forces it for every model of the process.
 ACCUMULATE_INTO_PARAM_GRAD = [False]
 
 # optional device-side timing of the MLP kernels (bench.py roofline): CUDA events on the launching stream
 PROFILE_ON = [False]
 PROFILE = []
+# MLP sample-evaluations issued through this module (forward calls, backward calls): bench.py's FLOP accounting
+EVALS = {"fwd": 0, "bwd": 0}
 
 
 class _timed:
@@ -60,6 +63,39 @@ def get_engine() -> int:
 
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_tensor_device(fn):
+    """Run an op body with the CUDA device of its first tensor argument current: the kernels launch on the current
+    device's current stream, so a Graph on cuda:1 works without a global torch.cuda.set_device (one process driving
+    several devices)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                dev = a.device
+                break
+            saved = getattr(a, "saved_tensors", None) if not torch.is_tensor(a) and hasattr(a, "needs_input_grad") else None
+            if saved:
+                cand = [t for t in saved if torch.is_tensor(t) and t.is_cuda]
+                if cand:
+                    dev = cand[0].device
+                    break
+        if dev is None:
+            for a in kwargs.values():
+                if torch.is_tensor(a) and a.is_cuda:
+                    dev = a.device
+                    break
+        if dev is None and kwargs.get("device") is not None:
+            dev = torch.device(kwargs["device"])
+        if dev is None or (torch.cuda.current_device() == (dev.index if dev.index is not None else torch.cuda.current_device())):
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
@@ -124,13 +160,19 @@ class MLPSpec:
 
 
 _WS = {}
+_WS_RETIRED = []   # outgrown buffers stay alive: a captured CUDA graph may have their addresses baked into its kernels
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch buffer (stream-ordered reuse is safe: one stream, no overlap)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """Grow-only per-(device, stream) scratch buffer.  Reuse is stream-ordered, so one buffer per stream is safe; a
+    buffer that is outgrown is retired, never freed (CUDA graphs captured earlier keep replaying into it)."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            _WS_RETIRED.append(buf)
+            nbytes = max(nbytes, int(1.5 * buf.numel()))   # geometric growth bounds the retired bytes
         buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
         _WS[key] = buf
     return buf
@@ -141,6 +183,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 class MLPFunction(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, spec: MLPSpec, engine: int, grad_mode: bool, origins, dirs, t, noise, progress, *params):
         L = _lib.lib()
         origins, dirs, t = _f32c(origins), _f32c(dirs), _f32c(t)
@@ -155,6 +198,7 @@ class MLPFunction(torch.autograd.Function):
         # Training forward: when a gradient will be asked for and the engine offers it, keep a "tape" (the
         # per-layer operand images) so that the backward skips the forward recompute.
         # (grad_mode: autograd is recording at the call site -- under torch.no_grad() nothing is kept)
+        EVALS["fwd"] += R * S
         wants_grad = grad_mode and (any(ctx.needs_input_grad[i] for i in (3, 4)) or any(ctx.needs_input_grad[8:]))
         tape_bytes = L.sparf_mlp_tape_bytes(ctypes.byref(m), engine, R, S) if (wants_grad and USE_TAPE[0]) else 0
         ctx.tape = None
@@ -170,7 +214,8 @@ class MLPFunction(torch.autograd.Function):
         ctx.spec, ctx.engine = spec, engine
         ctx.noise = noise_c
         ctx.progress = progress
-        ctx.param_refs = params if ACCUMULATE_INTO_PARAM_GRAD[0] else None
+        ctx.param_refs = params if (ACCUMULATE_INTO_PARAM_GRAD[0] or
+                                    all(getattr(p, "_sparf_inplace_grad", False) for p in params)) else None
         if ctx.tape is not None:
             ctx.save_for_backward(origins, dirs, t, sigma, rgb, *params)
         else:
@@ -178,6 +223,7 @@ class MLPFunction(torch.autograd.Function):
         return sigma, rgb
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g_sigma, g_rgb):
         L = _lib.lib()
         if ctx.tape is not None:
@@ -186,6 +232,7 @@ class MLPFunction(torch.autograd.Function):
             origins, dirs, t, *params = ctx.saved_tensors
         spec = ctx.spec
         R, S = t.shape
+        EVALS["bwd"] += R * S
         g_sigma = _f32c(g_sigma) if g_sigma is not None else torch.zeros(R, S, device=t.device)
         g_rgb = _f32c(g_rgb) if g_rgb is not None else torch.zeros(R, S, 3, device=t.device)
         m, keep = spec.fill(params, ctx.progress)
@@ -204,7 +251,7 @@ class MLPFunction(torch.autograd.Function):
         need_o, need_d = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         d_o = torch.zeros_like(origins) if (need_o or need_d) else None
         d_d = torch.zeros_like(dirs) if (need_o or need_d) else None
-        nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 1, ctx.engine)
+        nbytes = L.sparf_mlp_workspace_bytes(ctypes.byref(m), R, S, 2 if ctx.tape is not None else 1, ctx.engine)
         ws = _workspace(nbytes, t.device)
         with _timed("mlp_backward"):
             if ctx.tape is not None:
@@ -234,6 +281,7 @@ def mlp_forward(spec: MLPSpec, origins, dirs, t, params: Sequence[torch.Tensor],
 # ------------------------------------------------------------------------------------------------
 class CompositeFunction(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, sigma, rgb, t, dirs, white_bg: bool):
         L = _lib.lib()
         sigma, rgb, t, dirs = _f32c(sigma), _f32c(rgb), _f32c(t), _f32c(dirs)
@@ -252,6 +300,7 @@ class CompositeFunction(torch.autograd.Function):
         return rgb_map, depth, opacity, weights, depth_var, rgb_var, all_cum
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g_rgb, g_depth, g_opacity, g_weights, *_unused):
         L = _lib.lib()
         sigma, rgb, t, dirs = ctx.saved_tensors
@@ -277,6 +326,7 @@ def composite(sigma, rgb, t, dirs, white_bg=False):
 # ------------------------------------------------------------------------------------------------
 class RayGenFunction(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, pose_w2c, intr_inv, W: int, ray_idx, pixels):
         L = _lib.lib()
         pose_w2c, intr_inv = _f32c(pose_w2c), _f32c(intr_inv)
@@ -300,6 +350,7 @@ class RayGenFunction(torch.autograd.Function):
         return origins, dirs
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g_o, g_d):
         L = _lib.lib()
         pose_w2c, intr_inv, idx, pixels = ctx.saved_tensors
@@ -307,10 +358,13 @@ class RayGenFunction(torch.autograd.Function):
         d_pose = torch.zeros_like(pose_w2c)
         g_o = _f32c(g_o) if g_o is not None else None
         g_d = _f32c(g_d) if g_d is not None else None
+        # pixel locations are differentiable in the reference (camera.py:400-416); the depth-consistency loss renders at
+        # pixels projected from a rendered depth and back-propagates through them (depth_cons_loss.py:247-283)
+        d_px = torch.zeros_like(pixels) if (not ctx.has_idx and ctx.needs_input_grad[4]) else None
         check(L.sparf_raygen_backward(B, n, W, _ptr(pose_w2c), _ptr(intr_inv), _ptr(idx if ctx.has_idx else None),
                                       _ptr(None if ctx.has_idx else pixels), per_image, _ptr(g_o), _ptr(g_d),
-                                      _ptr(d_pose), _stream()), "raygen_backward")
-        return d_pose, None, None, None, None
+                                      _ptr(d_pose), _ptr(d_px), _stream()), "raygen_backward")
+        return d_pose, None, None, None, d_px
 
 
 _HOST_CACHE = {}
@@ -342,6 +396,7 @@ def raygen(pose_w2c, intr, W: int, *, ray_idx=None, pixels=None):
 # sampling (no gradient)
 # ------------------------------------------------------------------------------------------------
 @torch.no_grad()
+@_on_tensor_device
 def sample_depth(R: int, S: int, near: float, rng: float, *, inverse=False, rand=None, far_per_ray=None, device=None):
     L = _lib.lib()
     device = device or (rand.device if rand is not None else far_per_ray.device)
@@ -354,6 +409,7 @@ def sample_depth(R: int, S: int, near: float, rng: float, *, inverse=False, rand
 
 
 @torch.no_grad()
+@_on_tensor_device
 def sample_pdf_merge(weights, t_coarse, u_mid, near: float, far: float):
     """weights, t_coarse [R,S]; u_mid [S_fine] -> (t_fine [R,S_fine], t_all [R,S+S_fine] ascending)."""
     L = _lib.lib()
@@ -372,6 +428,7 @@ def sample_pdf_merge(weights, t_coarse, u_mid, near: float, far: float):
 # ------------------------------------------------------------------------------------------------
 class Huber2Function(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, pred, target):
         L = _lib.lib()
         pred_c, target_c = _f32c(pred), _f32c(target)
@@ -384,6 +441,7 @@ class Huber2Function(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         (d_pred,) = ctx.saved_tensors
         return (d_pred * g).view(ctx.shape), None
@@ -399,6 +457,7 @@ def huber2(pred, target):
 # ------------------------------------------------------------------------------------------------
 class DistortionFunction(torch.autograd.Function):
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, t, w):
         L = _lib.lib()
         t_c, w_c = _f32c(t), _f32c(w)
@@ -416,6 +475,7 @@ class DistortionFunction(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, g):
         d_w, d_t = ctx.saved_tensors
         return ((d_t * g).view(ctx.shapes[0]) if ctx.need_t else None), (d_w * g).view(ctx.shapes[1])

@@ -244,10 +244,17 @@ class Graph(torch.nn.Module):
                              inverse=(opt.nerf.depth.param == "inverse"), rand=rand, device=self.device)
         return t.view(batch_size, num_rays, n_samples, 1)
 
+    # renderer.py:439 draws the shared fine-sampling grid on the CPU generator and copies it over (a host->device
+    # copy per step).  device_side_rng = True -- and always while a CUDA graph is being captured, where a pageable
+    # host copy cannot be recorded -- draws the same U[0,1) grid with the device generator instead.
+    device_side_rng = False
+
     def _shared_grid_midpoints(self, n_samples_fine, det):
-        # renderer.py:435-442: one grid for all rays; the random one is drawn on the CPU generator
+        # renderer.py:435-442: one grid for all rays
         if det:
             grid = torch.linspace(0, 1, n_samples_fine + 1, device=self.device)
+        elif self.device_side_rng or torch.cuda.is_current_stream_capturing():
+            grid = torch.rand(n_samples_fine + 1, device=self.device)
         else:
             grid = torch.rand(n_samples_fine + 1).to(self.device)
         return 0.5 * (grid[:-1] + grid[1:])

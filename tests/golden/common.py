@@ -227,19 +227,43 @@ LOSS_CASES = {
     "c7_sparf_losses": dict(seed=7, B=3, H=24, W=32, n_rays=32, S=32, S_fine=32, fine=True, barf_c2f=(0.4, 0.7),
                             progress=0.5, depth_range=(1.2, 5.2), peaky=True, sigma_bias=-2.0, stratified=True,
                             rand_rays=96, min_nbr_matches=50, iteration=10),
+    # BASELINE config 4 flavour (LLFF): inverse depth, coarse network only, no c2f mask left (progress = 1), other seed
+    "c7b_sparf_losses_inverse": dict(seed=17, B=3, H=24, W=32, n_rays=32, S=48, S_fine=32, fine=False, barf_c2f=(0.4, 0.7),
+                                     progress=1.0, depth_param="inverse", depth_range=(1, 0), data_depth_range=(0.5, 8.0),
+                                     peaky=True, sigma_bias=-2.0, stratified=True, rand_rays=96, min_nbr_matches=50,
+                                     iteration=10),
+    # 4 views, metric depth, hierarchical, stage 1 of the joint schedule: the fine network is still off
+    # (ratio_start_fine_sampling_at_x), so the losses see coarse depth only
+    "c7c_sparf_losses_stage1": dict(seed=27, B=4, H=24, W=32, n_rays=24, S=32, S_fine=32, fine=True, barf_c2f=(0.1, 0.5),
+                                    progress=0.2, depth_range=(1.0, 4.5), peaky=True, sigma_bias=-1.0, stratified=True,
+                                    rand_rays=96, min_nbr_matches=50, iteration=10, ratio_start_fine=0.3),
+    # DS-NeRF sparse-depth loss (base_losses.py:326-402) next to the photometric term: per-image render at the pixels
+    # that have a COLMAP depth, more valid pixels than rand_rays // B in image 0 (randperm subsampling), none in image 2
+    "c9_colmap_depth": dict(seed=37, B=3, H=24, W=32, n_rays=24, S=32, S_fine=32, fine=True, barf_c2f=None,
+                            progress=None, depth_range=(1.2, 5.2), peaky=True, sigma_bias=-2.0, stratified=True,
+                            rand_rays=96, min_nbr_matches=50, iteration=10, colmap=True,
+                            loss_type="photometric_and_SparseCOLMAPDepthLoss"),
 }
 
 
 def loss_case_inputs(name):
     c = dict(LOSS_CASES[name])
     opt = make_opt(S=c["S"], S_fine=c["S_fine"], fine=c["fine"], depth_range=c["depth_range"], stratified=c["stratified"],
-                   barf_c2f=c["barf_c2f"], rand_rays=c["rand_rays"])
-    opt.loss_type = "photometric_and_corres_and_depth_cons"
+                   barf_c2f=c["barf_c2f"], rand_rays=c["rand_rays"], depth_param=c.get("depth_param", "metric"),
+                   ratio_start_fine=c.get("ratio_start_fine"))
+    opt.loss_type = c.get("loss_type", "photometric_and_corres_and_depth_cons")
     opt.loss_weight.corres = -3.0
     opt.loss_weight.depth_cons = -3.0
+    opt.loss_weight.colmap_depth = 0
     opt.min_nbr_matches = c["min_nbr_matches"]
     data = make_scene(c["seed"], c["B"], c["H"], c["W"])
-    data.depth_range = torch.tensor([list(map(float, c["depth_range"]))] * c["B"])
+    data.depth_range = torch.tensor([list(map(float, c.get("data_depth_range", c["depth_range"])))] * c["B"])
+    if c.get("colmap"):     # sparse "COLMAP" depth + confidence maps: [B,1,H,W], zero = no triangulated point
+        rng_c = np.random.default_rng(c["seed"] + 4000)
+        dm = rng_c.uniform(c["depth_range"][0] + 0.5, c["depth_range"][1] - 0.5, size=(c["B"], 1, c["H"], c["W"]))
+        keep = rng_c.uniform(size=dm.shape) < np.array([0.2, 0.02, 0.0]).reshape(-1, 1, 1, 1)[: c["B"]]
+        data.colmap_depth = torch.from_numpy((dm * keep).astype(np.float32))
+        data.colmap_conf = torch.from_numpy(rng_c.uniform(0.2, 1.0, size=dm.shape).astype(np.float32))
     rng = np.random.default_rng(c["seed"] + 3000)
     ray_idx = torch.from_numpy(rng.permutation(c["H"] * c["W"])[: c["n_rays"]].astype(np.int64))
     sd = det_weights(opt, c["seed"], peaky=c["peaky"], progress=c["progress"], sigma_bias=c["sigma_bias"])
@@ -276,6 +300,25 @@ CASES = {
     # render_to_max (depth-consistency visibility pass): per-ray far bound, both nets on same samples
     "c6_to_max": dict(seed=6, B=2, H=24, W=32, n_rays=16, S=64, S_fine=64, fine=True,
                       depth_range=(0.8, 4.0), peaky=True, mode="train", to_max=True, sigma_bias=-3.0),
+    # full-image inference through Graph.forward -> render_by_slices (renderer.py:347-381) in VAL mode: no stratified
+    # jitter, no sigma noise although both flags are on, deterministic fine grid (renderer.py:326, 404, 435)
+    "c10_val_full_image": dict(seed=10, B=2, H=12, W=16, n_rays=0, S=64, S_fine=64, fine=True, depth_range=(1.0, 4.5),
+                               peaky=True, mode="val", full_image=True, rand_rays=80, stratified=True, noise=True,
+                               sigma_bias=-2.0),
+    # same in EVAL mode, coarse only, inverse depth, opaque background, c2f mask mid-schedule
+    "c11_eval_full_image": dict(seed=11, B=1, H=12, W=16, n_rays=0, S=64, fine=False, depth_param="inverse",
+                                depth_range=(1, 0), peaky=True, mode="eval", full_image=True, rand_rays=64,
+                                stratified=True, setbg=True, barf_c2f=(0.1, 0.5), progress=0.35, sigma_bias=-2.0),
+    # test-time pose optimisation (joint_pose_nerf_trainer.py:381-404): mode "test-optim", random rays from
+    # Graph.forward, stratified + random fine grid, pose = se3 refinement o GT pose, gradient w.r.t. the 6-vector only
+    "c12_test_optim": dict(seed=12, B=1, H=24, W=32, n_rays=0, S=64, S_fine=64, fine=True, depth_range=(1.0, 4.5),
+                           peaky=True, mode="test-optim", test_optim=True, rand_rays=48, stratified=True,
+                           sigma_bias=-2.0),
+    # BASELINE config 5 flavour: 9 views, per-image (B,n) ray indices (RaySamplingStrategy, sampling_strategies.py:132),
+    # hierarchical, photometric loss gathers per image (base_losses.py:283-291)
+    "c13_b9_per_image_idx": dict(seed=13, B=9, H=20, W=24, n_rays=12, S=64, S_fine=64, fine=True,
+                                 depth_range=(0.1, 4.5), peaky=True, mode="train", per_image_idx=True,
+                                 sigma_bias=-2.0),
 }
 
 
@@ -285,12 +328,16 @@ def case_inputs(name):
     opt = make_opt(S=c["S"], S_fine=c.get("S_fine", 128), fine=c["fine"],
                           depth_param=c.get("depth_param", "metric"), depth_range=c["depth_range"],
                           stratified=c.get("stratified", False), noise=c.get("noise", False),
-                          barf_c2f=c.get("barf_c2f"), setbg=c.get("setbg", False))
+                          barf_c2f=c.get("barf_c2f"), setbg=c.get("setbg", False), rand_rays=c.get("rand_rays", 1024))
     data = make_scene(c["seed"], c["B"], c["H"], c["W"], identity=c.get("identity", False))
     data.depth_range = torch.tensor([list(map(float, c["depth_range"]))] * c["B"])
     rng = np.random.default_rng(c["seed"] + 3000)
     HW = c["H"] * c["W"]
     ray_idx = torch.from_numpy(rng.permutation(HW)[: c["n_rays"]].astype(np.int64))
+    if c.get("per_image_idx"):
+        ray_idx = torch.from_numpy(np.stack([rng.permutation(HW)[: c["n_rays"]] for _ in range(c["B"])]).astype(np.int64))
+    if c.get("depth_param") == "inverse" and c.get("full_image"):   # the dataset still carries a metric range; the renderer ignores it
+        data.depth_range = torch.tensor([[0.5, 8.0]] * c["B"])
     pixels = None
     if c.get("pixels"):
         px = rng.uniform([1, 1], [c["W"] - 2, c["H"] - 2], size=(c["B"], c["n_rays"], 2))
@@ -307,4 +354,6 @@ def case_inputs(name):
     if c.get("to_max"):
         dm = rng.uniform(c["depth_range"][0] + 0.3, c["depth_range"][1], size=(c["B"], c["n_rays"]))
         depth_max = torch.from_numpy(dm.astype(np.float32))
+    if c.get("test_optim"):     # non-zero se3 refinement so that the Lie exponential and its gradient are exercised
+        c["se3_refine"] = torch.from_numpy(rng.normal(0, 0.02, size=(1, 6)).astype(np.float32))
     return c, opt, data, ray_idx, pixels, sd, sd_fine, init_w2c, depth_max

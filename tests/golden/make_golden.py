@@ -59,14 +59,22 @@ class RandomRecorder:
         self.randperm_calls.append(x.clone())
         return x
 
+    def tensor(self, *a, **kw):
+        # The reference writes `torch.tensor(0., requires_grad=True).to(device)` and later `loss += ...`
+        # (base_losses.py:366-393).  On CUDA -- the only device the reference runs on -- `.to` copies, so the
+        # accumulator is a non-leaf; on this CPU-only box `.to` is the identity and the in-place add on a leaf raises.
+        # Reproduce the CUDA behaviour: hand out a non-leaf zero (same value, same arithmetic).
+        t = self._tensor(*a, **kw)
+        return t * 1.0 if (kw.get("requires_grad") and t.dim() == 0) else t
+
     def __enter__(self):
         self.randperm_calls = []
-        self._rand, self._randn_like, self._randperm = torch.rand, torch.randn_like, torch.randperm
-        torch.rand, torch.randn_like, torch.randperm = self.rand, self.randn_like, self.randperm
+        self._rand, self._randn_like, self._randperm, self._tensor = torch.rand, torch.randn_like, torch.randperm, torch.tensor
+        torch.rand, torch.randn_like, torch.randperm, torch.tensor = self.rand, self.randn_like, self.randperm, self.tensor
         return self
 
     def __exit__(self, *a):
-        torch.rand, torch.randn_like, torch.randperm = self._rand, self._randn_like, self._randperm
+        torch.rand, torch.randn_like, torch.randperm, torch.tensor = self._rand, self._randn_like, self._randperm, self._tensor
 
 
 class PoseGraph(ref_renderer.Graph):
@@ -80,11 +88,26 @@ class PoseGraph(ref_renderer.Graph):
         return self.pose_net.get_w2c_poses()
 
 
+class TestOptimGraph(ref_renderer.Graph):
+    """The test-time-optimisation branch of joint_pose_nerf_trainer.Graph.get_w2c_pose (:720-741) with the sim(3)
+    alignment left out (identity): pose = pose_refine_test o GT pose."""
+
+    def get_w2c_pose(self, opt, data_dict, mode=None):
+        from source.utils import camera as ref_camera
+        return ref_camera.pose.compose([data_dict.pose_refine_test, data_dict.pose])
+
+
 def run_case(name):
     c, opt, data, ray_idx, pixels, sd, sd_fine, init_w2c, depth_max = common.case_inputs(name)
     dev = torch.device("cpu")
     torch.manual_seed(0)
-    if c.get("pose_net"):
+    se3 = None
+    if c.get("test_optim"):
+        from source.utils import camera as ref_camera
+        net = TestOptimGraph(opt, dev)
+        se3 = torch.nn.Parameter(c["se3_refine"].clone())
+        data.pose_refine_test = ref_camera.lie.se3_to_SE3(se3)
+    elif c.get("pose_net"):
         pose_net = FirstTwoColunmnsPoseParameters(opt, nbr_poses=c["B"], initial_poses_w2c=init_w2c, device=dev)
         net = PoseGraph(opt, dev, pose_net)
     else:
@@ -96,7 +119,12 @@ def run_case(name):
 
     out_npz = {}
     with RandomRecorder(c["seed"]) as rec:
-        if c.get("to_max"):
+        if c.get("full_image"):
+            with torch.no_grad():   # val_step / evaluate_full: Graph.forward -> render_by_slices
+                out = net.forward(opt, data, iter=10, mode=c["mode"])
+        elif c.get("test_optim"):
+            out = net.forward(opt, data, iter=None, mode=c["mode"])
+        elif c.get("to_max"):
             pose = net.get_w2c_pose(opt, data, mode=c["mode"])
             out = net.render_up_to_maxdepth_at_specific_pose_and_rays(
                 opt, data, pose, data.intr, c["H"], c["W"], depth_max=depth_max, iter=10,
@@ -109,6 +137,14 @@ def run_case(name):
     # loss: the reference photometric module when rays come from ray_idx; for float pixels the
     # reference has no photometric target, so use a fixed linear functional of rgb/depth/opacity
     # (exercises the same gradients; the formula is restated in the tests).
+    if c.get("full_image"):
+        for k, v in out.items():
+            if isinstance(v, torch.Tensor) and k not in ("ray_idx", "idx_img_rendered"):
+                out_npz["out_" + k] = v.detach().numpy()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out_npz)
+        print("%-20s (forward only) keys=%d  %.1f KB" % (name, len(out_npz), os.path.getsize(path) / 1024))
+        return
     if pixels is None and not c.get("to_max"):
         loss_mod = BasePhotoandReguLoss(opt, net, train_data=None, device=dev)
         loss_dict, _, _ = loss_mod.compute_loss(opt, data, out, iteration=10, mode=c["mode"])
@@ -137,6 +173,10 @@ def run_case(name):
         out_npz["rand_%d" % i] = r.numpy()
     for i, r in enumerate(rec.randn_calls):
         out_npz["randn_%d" % i] = r.numpy()
+    for i, r in enumerate(rec.randperm_calls):
+        out_npz["randperm_%d" % i] = r.numpy()
+    if se3 is not None:
+        out_npz["grad_se3_refine"] = se3.grad.numpy()
 
     nets = [("nerf", net.nerf)] + ([("nerf_fine", net.nerf_fine)] if c["fine"] else [])
     for tag, m in nets:
@@ -183,7 +223,8 @@ def run_loss_case(name):
     pose_net = FirstTwoColunmnsPoseParameters(opt, nbr_poses=c["B"], initial_poses_w2c=init_w2c, device=dev)
     net = PoseGraph(opt, dev, pose_net)
     net.nerf.load_state_dict(sd)
-    net.nerf_fine.load_state_dict(sd_fine)
+    if c["fine"]:
+        net.nerf_fine.load_state_dict(sd_fine)
     net.train()
     train_data = edict(all=data)
     train_data.__class__.__len__ = lambda self: c["B"]
@@ -201,9 +242,11 @@ def run_loss_case(name):
         out_npz["rand_%d" % i] = r.numpy()
     for i, r in enumerate(rec.randperm_calls):
         out_npz["randperm_%d" % i] = r.numpy()
-    for tag, m in (("nerf", net.nerf), ("nerf_fine", net.nerf_fine)):
+    for tag, m in [("nerf", net.nerf)] + ([("nerf_fine", net.nerf_fine)] if c["fine"] else []):
         for pname, p in m.named_parameters():
             if pname == "progress":
+                continue
+            if p.grad is None:      # fine network still switched off by the schedule: no gradient
                 continue
             g = p.grad.numpy()
             key = "grad_%s.%s" % (tag, pname)
@@ -215,7 +258,9 @@ def run_loss_case(name):
                 out_npz[key + ".sumsq"] = np.float64((g.astype(np.float64) ** 2).sum())
     out_npz["grad_pose_embedding"] = net.pose_net.pose_embedding.grad.numpy()
     out_npz["out_rgb"] = out["rgb"].detach().numpy()
-    out_npz["out_depth_fine"] = out["depth_fine"].detach().numpy()
+    if "depth_fine" in out:
+        out_npz["out_depth_fine"] = out["depth_fine"].detach().numpy()
+    out_npz["out_depth"] = out["depth"].detach().numpy()
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out_npz)
     print("%-20s %s  %.1f KB" % (name, {k: round(float(v), 6) for k, v in out_npz.items() if k.startswith("loss_")},

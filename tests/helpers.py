@@ -41,12 +41,18 @@ def replay_oracle(name, dtype=torch.float32):
     cast = lambda x: x.to(dtype) if torch.is_floating_point(x) else x
     params = {k: cast(v).clone().requires_grad_(k != "progress") for k, v in sd.items()}
     params_f = {k: cast(v).clone().requires_grad_(k != "progress") for k, v in sd_fine.items()} if sd_fine else None
-    emb = None
+    emb = se3 = None
     if init_w2c is not None:
         emb = O.pose_to_d9(init_w2c).to(dtype).clone().requires_grad_(True)
         pose = O.d9_to_pose(emb)
+    elif c.get("test_optim"):    # pose = GT pose o exp(se3 refinement)  (joint_pose_nerf_trainer.py:381-404, :737-739)
+        se3 = c["se3_refine"].to(dtype).clone().requires_grad_(True)
+        pose = O.compose_pair(O.se3_to_SE3(se3), data.pose.to(dtype))
+        ray_idx = torch.from_numpy(gold["randperm_0"])[: opt.nerf.rand_rays // c["B"]]   # Graph.forward's draw
     else:
         pose = data.pose.to(dtype)
+    if c.get("full_image"):
+        ray_idx = None
     intr = data.intr.to(dtype)
     if pixels is not None:
         center, ray = O.rays_at_pixels(pose, intr, pixels.to(dtype))
@@ -54,8 +60,12 @@ def replay_oracle(name, dtype=torch.float32):
         center, ray = O.rays_from_ray_idx(pose, intr, c["H"], c["W"], ray_idx)
     rand, noise, noise_f, grid = case_randoms(c, gold)
     drange = opt.nerf.depth.range if opt.nerf.depth.param == "inverse" else data.depth_range[0]
+    if c.get("full_image"):     # val / eval: nothing random is drawn, slices of a full image = one big batch
+        with torch.no_grad():
+            out = O.render(opt, params, params_f, center, ray, drange, mode=c["mode"], iteration=10)
+        return out, None, {}, gold
     out = O.render(opt, params, params_f, center, ray, drange, mode=c["mode"], rand=rand,
-                   noise=noise, noise_fine=noise_f, grid_fine=grid, iteration=10,
+                   noise=noise, noise_fine=noise_f, grid_fine=grid, iteration=None if c.get("test_optim") else 10,
                    depth_max=depth_max.to(dtype) if depth_max is not None else None)
     if pixels is None and not c.get("to_max"):
         loss = O.photometric_loss(out, data.image.to(dtype), ray_idx)
@@ -75,6 +85,8 @@ def replay_oracle(name, dtype=torch.float32):
                 grads["grad_%s.%s" % (tag, k)] = v.grad
     if emb is not None:
         grads["grad_pose_embedding"] = emb.grad
+    if se3 is not None:
+        grads = {"grad_se3_refine": se3.grad}     # the only quantity test-time optimisation updates
     return out, loss, grads, gold
 
 
@@ -164,6 +176,14 @@ def build_graph(name, device="cuda"):
                 return self.pose_net.get_w2c_poses()
 
         net = PoseGraph(opt, dev, pose_net.to(dev))
+    elif c.get("test_optim"):
+        from sparf_b200 import camera as our_camera
+
+        class TestOptimGraph(Graph):   # the test-optim branch of joint_pose_nerf_trainer.Graph.get_w2c_pose
+            def get_w2c_pose(self, opt, data_dict, mode=None):
+                return our_camera.pose.compose([data_dict.pose_refine_test, data_dict.pose])
+
+        net = TestOptimGraph(opt, dev)
     else:
         net = Graph(opt, dev)
     net.nerf.load_state_dict(sd)
@@ -182,8 +202,20 @@ def replay_graph(name, engine="simt_fp32"):
     sparf_b200.set_engine(engine)
     gold = load_golden(name)
     net, c, opt, data, ray_idx, pixels, depth_max = build_graph(name)
+    se3 = None
+    if c.get("test_optim"):
+        from sparf_b200 import camera as our_camera
+        se3 = torch.nn.Parameter(c["se3_refine"].clone().cuda())
+        data.pose_refine_test = our_camera.lie.se3_to_SE3(se3)
     with RandomReplayer(gold):
-        if c.get("to_max"):
+        if c.get("full_image"):
+            with torch.no_grad():
+                out = net.forward(opt, data, iter=10, mode=c["mode"])
+            return out, None, {}, gold
+        elif c.get("test_optim"):
+            out = net.forward(opt, data, iter=None, mode=c["mode"])
+            ray_idx = out.ray_idx
+        elif c.get("to_max"):
             pose = net.get_w2c_pose(opt, data, mode=c["mode"])
             out = net.render_up_to_maxdepth_at_specific_pose_and_rays(
                 opt, data, pose, data.intr, c["H"], c["W"], depth_max=depth_max, iter=10, ray_idx=ray_idx, mode=c["mode"])
@@ -210,4 +242,6 @@ def replay_graph(name, engine="simt_fp32"):
                 grads["grad_%s.%s" % (tag, pname)] = p.grad
     if hasattr(net, "pose_net"):
         grads["grad_pose_embedding"] = net.pose_net.pose_embedding.grad
+    if se3 is not None:
+        grads = {"grad_se3_refine": se3.grad}
     return out, loss, grads, gold

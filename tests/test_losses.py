@@ -59,24 +59,67 @@ def test_sample_rays_and_nearest_pose_cpu():
     assert L.get_nearest_pose_ids(poses[0], poses, tar_id=0) == 1
 
 
+def _loss_case_setup(name, dev):
+    gold = load_golden(name)
+    c, opt, data, ray_idx, sd, sd_fine, init_w2c = common.loss_case_inputs(name)
+    for k in ("image", "intr", "pose", "depth_range", "idx", "colmap_depth", "colmap_conf"):
+        if k in data:
+            data[k] = data[k].to(dev)
+    return gold, c, opt, data, ray_idx.to(dev), sd, sd_fine, init_w2c.to(dev)
+
+
+class _TrainData:
+    def __init__(self, d, n):
+        self.all, self.n = d, n
+
+    def __len__(self):
+        return self.n
+
+
+def _run_and_check(name, engine, gold, c, opt, data, ray_idx, net, loss_module, pose_embedding, gtol):
+    with RandomReplayer(gold):
+        data["iter"] = c["iteration"]
+        out = net.render_image_at_specific_rays(opt, data, iter=c["iteration"], ray_idx=ray_idx, mode="train")
+        data.poses_w2c = net.get_w2c_pose(opt, data, mode="train")
+        loss_dict, stats, _ = loss_module.compute_loss(opt, data, out, iteration=c["iteration"], mode="train")
+    loss_dict["all"].backward()
+    torch.cuda.synchronize()
+    rep = {}
+    for k in [k[5:] for k in gold if k.startswith("loss_") and not k.endswith("_after_w")]:
+        ref = float(gold["loss_" + k])
+        got = float(loss_dict[k])
+        rep[k] = abs(got - ref) / max(abs(ref), 1e-6)
+        # correspondence / depth-consistency / sparse-depth terms sit behind hierarchical resampling and data-dependent
+        # point selection (visibility >= 0.2); inverse depth adds its conditioning (test_oracle_vs_golden.py):
+        # 2e-3; the photometric term and the total: 2e-4 (metric depth)
+        loose = k in ("corres", "depth_cons", "colmap_depth") or c.get("depth_param") == "inverse"
+        assert rep[k] < (2e-3 if loose else 2e-4), (name, k, got, ref)
+    grads = {}
+    for tag, m in [("nerf", net.nerf)] + ([("nerf_fine", net.nerf_fine)] if c["fine"] else []):
+        for pname, p in m.named_parameters():
+            if pname != "progress" and ("grad_%s.%s" % (tag, pname) in gold or "grad_%s.%s.sub" % (tag, pname) in gold):
+                grads["grad_%s.%s" % (tag, pname)] = p.grad
+    grads["grad_pose_embedding"] = pose_embedding.grad
+    worst = check_grads(grads, gold, tol=gtol)
+    print(name, engine, {k: "%.1e" % v for k, v in rep.items()}, "worst grad %.1e" % worst)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("engine", ["simt_fp32", "tc_3x"])
-def test_full_sparf_step_vs_reference(engine):
-    """photometric + corres + depth-cons on our Graph/losses vs the reference's modules on its Graph."""
+@pytest.mark.parametrize("name", list(common.LOSS_CASES))
+def test_full_sparf_step_vs_reference(name, engine):
+    """photometric + corres + depth-cons (+ the DS-NeRF sparse-depth case) on our Graph / loss mirrors vs the reference's
+    modules on its Graph (goldens: tests/golden/make_golden.py run_loss_case).  The depth-consistency term
+    back-propagates through the float pixel locations of its second render (raygen d_pixels)."""
     import sparf_b200
     from sparf_b200.losses import define_loss
     from sparf_b200.poses_models import FirstTwoColunmnsPoseParameters
     from sparf_b200.renderer import Graph
-    from sparf_b200.utils.edict import edict
 
-    name = "c7_sparf_losses"
     sparf_b200.set_engine(engine)
-    gold = load_golden(name)
-    c, opt, data, ray_idx, sd, sd_fine, init_w2c = common.loss_case_inputs(name)
     dev = torch.device("cuda")
-    for k in ("image", "intr", "pose", "depth_range", "idx"):
-        data[k] = data[k].to(dev)
-    pose_net = FirstTwoColunmnsPoseParameters(opt, nbr_poses=c["B"], initial_poses_w2c=init_w2c.to(dev), device=dev).to(dev)
+    gold, c, opt, data, ray_idx, sd, sd_fine, init_w2c = _loss_case_setup(name, dev)
+    pose_net = FirstTwoColunmnsPoseParameters(opt, nbr_poses=c["B"], initial_poses_w2c=init_w2c, device=dev).to(dev)
 
     class PoseGraph(Graph):
         def __init__(self, opt, device, pose_net):
@@ -88,39 +131,48 @@ def test_full_sparf_step_vs_reference(engine):
 
     net = PoseGraph(opt, dev, pose_net)
     net.nerf.load_state_dict(sd)
-    net.nerf_fine.load_state_dict(sd_fine)
+    if c["fine"]:
+        net.nerf_fine.load_state_dict(sd_fine)
     net.to(dev).train()
-
-    class TrainData:
-        def __init__(self, d):
-            self.all = d
-
-        def __len__(self):
-            return c["B"]
-
     flow = common.FakeFlowNet(c["B"], c["H"], c["W"])
     np.random.seed(c["seed"])
-    with RandomReplayer(gold):
-        loss_module = define_loss(opt.loss_type, opt, net, TrainData(data), dev, flow_net=flow)
-        data["iter"] = c["iteration"]
-        out = net.render_image_at_specific_rays(opt, data, iter=c["iteration"], ray_idx=ray_idx.to(dev), mode="train")
-        data.poses_w2c = net.get_w2c_pose(opt, data, mode="train")
-        loss_dict, stats, _ = loss_module.compute_loss(opt, data, out, iteration=c["iteration"], mode="train")
-    loss_dict["all"].backward()
-    torch.cuda.synchronize()
-    rep = {}
-    for k in ("render", "corres", "depth_cons", "all"):
-        ref = float(gold["loss_" + k])
-        got = float(loss_dict[k])
-        rep[k] = abs(got - ref) / max(abs(ref), 1e-6)
-        # correspondence / depth-consistency terms sit behind hierarchical resampling and data-dependent
-        # point selection (visibility >= 0.2): 2e-3; the photometric term and the total: 2e-4
-        assert rep[k] < (2e-3 if k in ("corres", "depth_cons") else 2e-4), (k, got, ref)
-    grads = {}
-    for tag, m in (("nerf", net.nerf), ("nerf_fine", net.nerf_fine)):
-        for pname, p in m.named_parameters():
-            if pname != "progress":
-                grads["grad_%s.%s" % (tag, pname)] = p.grad
-    grads["grad_pose_embedding"] = net.pose_net.pose_embedding.grad
-    worst = check_grads(grads, gold, tol=6e-2)
-    print(engine, {k: "%.1e" % v for k, v in rep.items()}, "worst grad %.1e" % worst)
+    loss_module = define_loss(opt.loss_type, opt, net, _TrainData(data, c["B"]), dev, flow_net=flow)
+    # gradient bound: the reference's own fp32 gradients sit ~3e-2 from the exact ones on these nets (conditioning,
+    # test_tc_engine.py); inverse depth: 0.25 as for golden c4
+    _run_and_check(name, engine, gold, c, opt, data, ray_idx, net, loss_module, pose_net.pose_embedding,
+                   gtol=0.25 if c.get("depth_param") == "inverse" else 6e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c7_sparf_losses", "c9_colmap_depth"])
+def test_reference_trainer_graph_and_losses_on_our_renderer(name):
+    """THE DROP-IN PROOF.  The reference's OWN `joint_pose_nerf_trainer.Graph` subclass (:710-749), its own pose model
+    and its own `loss_factory.define_loss` modules run UNCHANGED with `source.models.renderer` resolved to
+    `sparf_b200.renderer` (oracle/ref_loader.py shadow_renderer=True): every render they trigger goes through the CUDA
+    kernels, and the losses / gradients must match the goldens the unmodified reference produced on its own renderer."""
+    from oracle import ref_loader
+    if not ref_loader.ref_root():
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py in the build container)")
+    import sparf_b200
+    import sparf_b200.renderer as our_renderer
+
+    sparf_b200.set_engine("auto")
+    ref = ref_loader.load("trainer", shadow_renderer=True)
+    try:
+        assert issubclass(ref.joint.Graph, our_renderer.Graph) and ref.joint.Graph is not our_renderer.Graph
+        dev = torch.device("cuda")
+        gold, c, opt, data, ray_idx, sd, sd_fine, init_w2c = _loss_case_setup(name, dev)
+        pose_net = ref.two_columns.FirstTwoColunmnsPoseParameters(opt, nbr_poses=c["B"], initial_poses_w2c=init_w2c, device=dev)
+        net = ref.joint.Graph(opt, dev, pose_net)
+        net.nerf.load_state_dict(sd)
+        if c["fine"]:
+            net.nerf_fine.load_state_dict(sd_fine)
+        net.to(dev).train()
+        flow = common.FakeFlowNet(c["B"], c["H"], c["W"])
+        np.random.seed(c["seed"])
+        loss_module = ref.loss_factory.define_loss(opt.loss_type, opt, net, _TrainData(data, c["B"]), dev, flow_net=flow)
+        assert type(loss_module).__module__.startswith("source.training.core")
+        _run_and_check(name, "reference trainer Graph + reference losses over sparf_b200 (auto engine)", gold, c, opt, data,
+                       ray_idx, net, loss_module, pose_net.pose_embedding, gtol=6e-2)
+    finally:
+        ref_loader._purge()

@@ -122,7 +122,10 @@ def test_tcgen05_selftest_tn_mn_major(rows):
     assert torch.equal(D, ref), (D - ref).abs().max().item()
 
 
-@pytest.mark.parametrize("R,S,c2f", [(8, 128, None), (1023, 128, None), (100, 96, (0.4, 0.7)), (37, 384, None)])
+# the last three batches exceed one backward chunk (1024 row tiles): the taped forward keeps ONE tape and the backward
+# walks it chunk by chunk (tile-aligned chunk starts, accumulating gradients); the recompute path chunks as well
+@pytest.mark.parametrize("R,S,c2f", [(8, 128, None), (1023, 128, None), (100, 96, (0.4, 0.7)), (37, 384, None),
+                                     (1100, 128, None), (600, 256, (0.4, 0.7)), (1400, 96, None)])
 def test_tc_backward_matches_simt(R, S, c2f):
     """tcgen05 backward (bf16 3-pass recompute + dgrad chain + MN-major wgrad) vs the fp32 SIMT engine:
     every parameter gradient, same upstream gradients, same device inputs."""
@@ -170,7 +173,7 @@ def test_tc_backward_matches_simt(R, S, c2f):
     print("R=%d S=%d: worst grad rel err vs fp64: tcgen05 %.2e, simt fp32 %.2e" % (R, S, worst_tc, worst_simt))
 
 
-@pytest.mark.parametrize("R,S,c2f", [(64, 128, None), (341, 128, (0.4, 0.7)), (50, 96, (0.1, 0.9))])
+@pytest.mark.parametrize("R,S,c2f", [(64, 128, None), (341, 128, (0.4, 0.7)), (50, 96, (0.1, 0.9)), (1100, 128, (0.4, 0.7))])
 def test_tc_ray_gradients_match_simt(R, S, c2f):
     """dL/d origins, dL/d dirs (camera-pose optimisation) from the tcgen05 path (G4.W4e + G0.W0 on tensor
     cores + encoding backward in the epilogue + view-direction chain) vs the fp32 SIMT engine."""
