@@ -197,12 +197,17 @@ def build_problem(cfg_name, impl, device, seed=0, stratified=True):
     pr = argparse.Namespace(cfg=cfg, opt=opt, data=data, net=net, pose_net=pose_net, loss_module=loss_module,
                             modules=modules, iteration=10)
 
+    needs_poses = "corres" in cfg["loss_type"] or "depth_cons" in cfg["loss_type"]
+
     def forward_backward(ray_idx):
         data["iter"] = pr.iteration
         out = net.render_image_at_specific_rays(opt, data, iter=pr.iteration, ray_idx=ray_idx, mode="train")
-        data.poses_w2c = net.get_w2c_pose(opt, data, mode="train")
+        if needs_poses:     # nerf_trainer.py:239-240: the current pose estimates, with their autograd history
+            data.poses_w2c = net.get_w2c_pose(opt, data, mode="train")
         loss = loss_module.compute_loss(opt, data, out, iteration=pr.iteration, mode="train")[0]["all"]
         loss.backward()
+        if needs_poses:     # do not keep the step's autograd graph alive into the next step (or a graph capture)
+            data.pop("poses_w2c", None)
         return loss.detach()
 
     pr.forward_backward = forward_backward

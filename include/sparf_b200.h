@@ -210,6 +210,8 @@ int sparf_tc_selftest(const float* A, const float* B, int32_t K, void* packed, f
 int sparf_tc_selftest_ts(const float* A, const float* B, int32_t K, void* packed, float* D, sparf_stream_t stream);
 /* Same for the weight-gradient shape: D[128,128] = G[rows,128]^T X[rows,128] through MN-major descriptors. */
 int sparf_tc_selftest_tn(const float* G, const float* X, int32_t rows, float* D, sparf_stream_t stream);
+/* probe: same with G in bf16 and X in fp16 (mixed operand formats in one kind::f16 instruction) */
+int sparf_tc_selftest_tn_mixed(const float* G, const float* X, int32_t rows, float* D, sparf_stream_t stream);
 
 /* Micro-benchmark of cp.async.bulk L2->shared throughput per SM vs copies in flight (tools/probe_bulkcopy.py). */
 int sparf_tc_bulkcopy_probe(const void* src, uint32_t src_bytes, int32_t stages, uint32_t chunk, int32_t iters,

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "sparf_tc_selftest": (c_int32, [_P, _P, c_int32, _P, _P, _P]),
     "sparf_tc_selftest_ts": (c_int32, [_P, _P, c_int32, _P, _P, _P]),
     "sparf_tc_selftest_tn": (c_int32, [_P, _P, c_int32, _P, _P]),
+    "sparf_tc_selftest_tn_mixed": (c_int32, [_P, _P, c_int32, _P, _P]),
     "sparf_tc_bulkcopy_probe": (c_int32, [_P, ctypes.c_uint32, c_int32, ctypes.c_uint32, c_int32, c_int32, _P, _P]),
 }
 
@@ -76,7 +77,12 @@ def lib():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.exists(path) or _build._stale():
+    override = os.environ.get("SPARF_B200_LIB")     # debug builds (python -m sparf_b200.build --trace), tools only
+    if override:
+        if not os.path.exists(override):
+            raise RuntimeError("SPARF_B200_LIB=%s does not exist" % override)
+        path = override
+    elif not os.path.exists(path) or _build._stale():
         try:
             path = _build.build()
         except Exception as e:  # no nvcc on this box and no prebuilt library: nothing to run

@@ -45,15 +45,25 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library.  Returns its path."""
-    if not force and not _stale():
+TRACE_LIB_PATH = os.path.join(LIB_DIR, "libsparf_b200_trace.so")   # debug build (tools/trace_chain.py), never loaded by default
+
+
+def build(force: bool = False, verbose: bool = False, trace: bool = False, variant: str = "", defines_extra=()) -> str:
+    """Compile every .cu under csrc/ into one shared library.  Returns its path.  trace=True builds the wait-time
+    tracing variant (-DSPARF_TC_TRACE) next to it; `SPARF_B200_LIB=<path>` makes sparf_b200._lib load that instead."""
+    out_path = TRACE_LIB_PATH if trace else LIB_PATH
+    if variant:     # experiment builds: lib/libsparf_b200_<variant>.so with extra -D flags (tools only, via SPARF_B200_LIB)
+        out_path = os.path.join(LIB_DIR, "libsparf_b200_%s.so" % variant)
+    if not trace and not variant and not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = sources()
     defines = ["-DSPARF_WITH_TC"] if os.path.exists(os.path.join(CSRC, "mlp_tc.cu")) else []
-    defines += os.environ.get("SPARF_NVCC_DEFINES", "").split()   # e.g. -DSPARF_TC_TRACE (debug builds only)
-    cmd = [_nvcc()] + NVCC_FLAGS + defines + ["-I", INCLUDE, "-o", LIB_PATH + ".tmp"] + srcs
+    defines += os.environ.get("SPARF_NVCC_DEFINES", "").split()   # extra debug defines
+    if trace:
+        defines.append("-DSPARF_TC_TRACE")
+    defines += list(defines_extra)
+    cmd = [_nvcc()] + NVCC_FLAGS + defines + ["-I", INCLUDE, "-o", out_path + ".tmp"] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -63,9 +73,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libsparf_b200.so")
     if verbose:
         print(res.stdout + res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    return LIB_PATH
+    os.replace(out_path + ".tmp", out_path)
+    return out_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    _defs = sys.argv[sys.argv.index("--defines") + 1].split() if "--defines" in sys.argv else []
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv, variant=_variant,
+                defines_extra=_defs))

@@ -87,7 +87,8 @@ constexpr int kOffW9 = kOffW7r0 + 256 * 4;               // 3 x 128 floats
 constexpr int kOffMisc = kOffW9 + 3 * 128 * 4;           // b7[0], b9[0..2], c2f weights [16]
 constexpr int kOffPart = kOffMisc + 32 * 4;              // 3 x 128 x 4 floats: partial dots of column quarters 1..3
 constexpr int kOffBar = kOffPart + 3 * 128 * 4 * 4;      // mbarriers
-constexpr int kNumBars = 3 * kMaxStages + 5 + 4 + 8;
+constexpr int kMaxSlots = 8;                              // image staging slots (g_ready / s_free barrier pairs)
+constexpr int kNumBars = 3 * kMaxStages + 5 + 4 + 2 * kMaxSlots;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 constexpr int kOffBarBwd = kOffEnc + kBwdStages * kChunkBytes;   // dgrad: barriers right after its ring
 static_assert(kOffBarBwd + kNumBars * 8 + 16 <= kSmemBytes, "dgrad shared-memory map exceeds the launch size");
@@ -335,7 +336,7 @@ __device__ __forceinline__ void store16(const Split16& v, int row, int col0, uin
 // wait-time accounting of the warp roles (only with -DSPARF_TC_TRACE; see tools/trace_chain.py)
 struct Trace { long long w[4]; long long t0; int n; };
 #ifdef SPARF_TC_TRACE
-__device__ long long g_tc_trace[148 * 4 * 8];
+__device__ long long g_tc_trace[148 * 6 * 8];
 __device__ long long g_tc_events[512 * 8];   // CTA 0, first 512 weight chunks: producer / issuer timestamps
 __device__ __forceinline__ void trace_begin(Trace& tr) { tr.w[0] = tr.w[1] = tr.w[2] = tr.w[3] = 0; tr.n = 0; tr.t0 = clock64(); }
 __device__ __forceinline__ void trace_event(long long g, int k) {
@@ -350,7 +351,7 @@ __device__ __forceinline__ long long trace_tic() { return clock64(); }
 __device__ __forceinline__ void trace_toc(Trace& tr, int cat, long long t0) { tr.w[cat] += clock64() - t0; }
 __device__ __forceinline__ void trace_end(const Trace& tr, int role) {
   if (blockIdx.x < 148) {
-    long long* o = g_tc_trace + ((size_t)blockIdx.x * 4 + role) * 8;
+    long long* o = g_tc_trace + ((size_t)blockIdx.x * 6 + role) * 8;
     o[0] = tr.w[0]; o[1] = tr.w[1]; o[2] = tr.w[2]; o[3] = tr.w[3]; o[4] = clock64() - tr.t0;
   }
 }
@@ -385,7 +386,7 @@ __device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem, int ring_off, in
   s.d_empty = s.d_full + 2;
   s.w_peer = s.d_empty + 2;
   s.g_ready = s.w_peer + kMaxStages;
-  s.s_free = s.g_ready + 4;
+  s.s_free = s.g_ready + kMaxSlots;
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   return s;
 }
@@ -401,7 +402,7 @@ __device__ __forceinline__ void chain_init_barriers(const ChainSmem& s, int ncta
     mbar_init(&s.w_peer[i], 1);
   }
   for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps * ncta);
-  for (int i = 0; i < 4; ++i) { mbar_init(&s.g_ready[i], kEpiWarps); mbar_init(&s.s_free[i], 1); }
+  for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&s.g_ready[i], kEpiWarps); mbar_init(&s.s_free[i], 1); }
   // d_full: one commit per issuer warp (stand-alone) or the leader's multicast commit (pair)
   for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], ncta == 1 ? n_issuers : 1); mbar_init(&s.d_empty[i], kEpiWarps * ncta); }
   fence_barrier_init();
@@ -661,9 +662,36 @@ __device__ __forceinline__ void chain_issue_single_ts(const ChainSmem& s, uint32
 //         images + an 8-stage weight ring; inference: a 10-stage ring | bias / small weights / barriers as before
 // One issuer warp (M128 x N256 MMAs over paired ring stages), the epilogue drains its whole share of the accumulator
 // into registers and frees it at once; warp 19 streams the tape images out of the staging slots with bulk copies.
+// Image staging (taped forward: kFwdSlots x 16 KB, one (block, part) each; dgrad: kDgSlots x 32 KB, one block's hi | lo).
+// The store warp keeps up to kStoreInflight bulk stores in flight: a slot is handed back to the epilogue warps when the
+// store issued kStoreInflight - 1 steps later has been committed and `cp.async.bulk.wait_group.read` reports its
+// predecessors' sources read.  Measured (profiles/r02_notes.md): one store at a time costs ~1000 clk per 16 KB copy and
+// the epilogue warps wait 12 % (forward) / 19 % (dgrad) of the kernel for a free slot -- yet trading ring stages for
+// slots (forward 5 slots + 6 stages, dgrad 3 + 8) or keeping 2-3 stores in flight measured SLOWER (taped forward 435 ->
+// 453..461 us, dgrad 291 -> 312..370 us): the weight ring's depth is worth more than the slots.  Defaults = 3 / 8, 2 / 10, 1.
+#ifndef SPARF_FWD_SLOTS
+#define SPARF_FWD_SLOTS 3
+#endif
+#ifndef SPARF_FWD_RING
+#define SPARF_FWD_RING 8
+#endif
+#ifndef SPARF_DG_SLOTS
+#define SPARF_DG_SLOTS 2
+#endif
+#ifndef SPARF_DG_RING
+#define SPARF_DG_RING 10
+#endif
+#ifndef SPARF_STORE_INFLIGHT
+#define SPARF_STORE_INFLIGHT 1
+#endif
+constexpr int kFwdSlots = SPARF_FWD_SLOTS, kDgSlots = SPARF_DG_SLOTS, kStoreInflight = SPARF_STORE_INFLIGHT;
+static_assert(kFwdSlots <= kMaxSlots && kDgSlots <= kMaxSlots && kStoreInflight >= 1 && kStoreInflight < kFwdSlots &&
+              kStoreInflight < kDgSlots, "staging slots / stores in flight");
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 constexpr int kOffEncT = 0;
 constexpr int kOffStgT = 2 * kChunkBytes;
-constexpr int kOffRingTSave = kOffStgT + 3 * kChunkBytes, kStagesTSave = 8;
+constexpr int kOffRingTSave = kOffStgT + kFwdSlots * kChunkBytes, kStagesTSave = SPARF_FWD_RING;
+static_assert(kStagesTSave % 2 == 0 && SPARF_DG_RING % 2 == 0, "N = 256 MMAs pair adjacent ring stages");
 constexpr int kOffRingTInf = 2 * kChunkBytes, kStagesTInf = 10;
 static_assert(kOffRingTSave + kStagesTSave * kChunkBytes <= kOffBias && kOffRingTInf + kStagesTInf * kChunkBytes <= kOffBias,
               "tensor-memory-operand forward: shared-memory map");
@@ -832,26 +860,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
     // streams the bf16 tape images of layers 0..7 out of the three rotating staging slots (one 16 KB block each)
     if (p.save) {
       uint8_t* stg = smem + kOffStgT;
+      Trace tr; trace_begin(tr);
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         for (int l = 0; l < 8; ++l) {
           const int t_img = l == 7 ? T_FEAT : T_H0 + l;
           for (int jp = 0; jp < 8; ++jp) {                         // (block j, part)
             const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + (uint32_t)jp;
-            const uint32_t slot = qs % 3u, k = qs / 3u;
-            mbar_wait(&cs.g_ready[slot], k & 1);
+            const uint32_t slot = qs % (uint32_t)kFwdSlots, k = qs / (uint32_t)kFwdSlots;
+            twait(tr, 0, &cs.g_ready[slot], k & 1);
+            long long t0 = trace_tic();
             if (elect_one()) {
               bulk_s2g(p.img.at(t_img, tile, jp >> 1, jp & 1), stg + (size_t)slot * kChunkBytes, kChunkBytes);
               bulk_commit_group();
-              bulk_wait_read_all();
-              mbar_arrive(&cs.s_free[slot]);
+              bulk_wait_read<kStoreInflight - 1>();      // every store but the newest kStoreInflight - 1 has read its slot
+              if (qs + 1u >= (uint32_t)kStoreInflight)
+                mbar_arrive(&cs.s_free[(qs + 1u - (uint32_t)kStoreInflight) % (uint32_t)kFwdSlots]);
             }
             __syncwarp();
+            trace_toc(tr, 1, t0);
           }
         }
       }
       if (elect_one()) bulk_wait_all();
       __syncwarp();
+      if (lane == 0) trace_end(tr, 4);
     }
   } else if (warp < 2 + kEpiWarps) {
     // ============================== epilogue warps ==============================
@@ -876,6 +909,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
 
       // ---------------- positional encoding -> A_enc (internal column order: x y z 0 | (sin,cos) pairs)
       {
+        long long tenc = trace_tic();
         float x[3] = {0.f, 0.f, 0.f};
         if (valid) {
           float tv = p.t[m];
@@ -908,6 +942,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
           if (kF16) split16<false>(vals, sp);
           store16_image(sp, row, cq * kEpiCols, p.img.at(T_ENC, tile, 0, 0), p.img.at(T_ENC, tile, 0, 1));
         }
+        trace_toc(tr, 3, tenc);
       }
 
       // ---------------- layers
@@ -922,16 +957,73 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
         uint32_t vn[16];                            // accumulator columns of the NEXT block, loaded one block ahead
         uint32_t va[kTmemA ? 4 : 1][16];            // kTmemA: this thread's whole share of the accumulator
         if (kTmemA) {
+          long long tld = trace_tic();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (j < nchunk) tmem_ld16(tmem_base + t_lane + (uint32_t)(j * 64 + cq * kEpiCols), va[j]);
           tmem_ld_wait();
+          trace_toc(tr, 2, tld);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&cs.d_empty[0]);   // the (single) accumulator is free for the next layer's MMAs
         } else {
           tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
         }
+        if (kTmemA && l < 8) {
+          // ---- phase 1 (critical path): bias + ReLU -> fp16 (hi, lo) -> tensor memory, block by block; the MMA warp
+          // starts layer l + 1 on K block j as soon as block j is in.  The activations stay in va[] for phase 2.
+          const float* bl_ = s_bias + l * 256 + cq * kEpiCols;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              f[i] = fmaxf(__uint_as_float(va[j][i]) + bl_[j * 64 + i], 0.f);
+              va[j][i] = __float_as_uint(f[i]);
+            }
+            Split16 sp;
+            split16<kF16>(f, sp);
+            tmem_st8(tmem_base + t_lane + 256u + (uint32_t)(j * 32 + cq * 8), sp.hi);
+            tmem_st8(tmem_base + t_lane + 384u + (uint32_t)(j * 32 + cq * 8), sp.lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+          }
+          // ---- phase 2 (overlaps the next layer's MMAs): density row, ReLU masks, bf16 tape through the staging slots
+          if (l == 6 || save) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col0 = j * 64 + cq * kEpiCols;
+              float f[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(va[j][i]);
+              if (l == 6) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dot0 = fmaf(f[i], s_w7r0[col0 + i], dot0);
+              }
+              if (save) {
+                uint32_t m16 = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) m16 |= (f[i] > 0.f ? 1u : 0u) << i;
+                mbits[j >> 1] |= m16 << (16 * (j & 1));
+                Split16 sp;
+                split16<false>(f, sp);
+                uint8_t* stg = smem + kOffStgT;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                  const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + 2u * (uint32_t)j + (uint32_t)part;
+                  const uint32_t slot = qs % (uint32_t)kFwdSlots, k = qs / (uint32_t)kFwdSlots;
+                  if (k > 0) twait(tr, 1, &cs.s_free[slot], (k - 1) & 1);
+                  store16_part(part == 0 ? sp.hi : sp.lo, row, cq * kEpiCols, stg + (size_t)slot * kChunkBytes);
+                  fence_proxy_async_smem();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
+                }
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (j >= nchunk) break;
@@ -998,8 +1090,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
 #pragma unroll
               for (int part = 0; part < 2; ++part) {
                 const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + 2u * (uint32_t)j + (uint32_t)part;
-                const uint32_t slot = qs % 3u, k = qs / 3u;
-                if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
+                const uint32_t slot = qs % (uint32_t)kFwdSlots, k = qs / (uint32_t)kFwdSlots;
+                if (k > 0) twait(tr, 1, &cs.s_free[slot], (k - 1) & 1);
                 store16_part(part == 0 ? sp.hi : sp.lo, row, cq * kEpiCols, stg + (size_t)slot * kChunkBytes);
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -1019,6 +1111,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
             }
           }
         }
+        }   // (shared-memory-operand kernels and the colour-head layer)
         // accumulator drained: hand it back to the MMA warp (kTmemA did so right after loading it)
         if (!kTmemA) {
           tc_fence_before();
@@ -1083,7 +1176,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
   const float* __restrict__ s_w9 = p.w9;
   // kTmemA: the activation blocks are no MMA operands any more, only a staging area for the image stores: two rotating
   // (hi, lo) block pairs (64 KB) are enough and the weight ring takes the rest: 10 stages = 5 [256 x 64] operands
-  const ChainSmem cs = kTmemA ? chain_carve(smem, kOffAct + 4 * kChunkBytes, 10, kOffBarBwd)
+  static_assert(kOffAct + kDgSlots * 2 * kChunkBytes + SPARF_DG_RING * kChunkBytes <= kOffBarBwd, "dgrad (TMEM operand) shared-memory map");
+  const ChainSmem cs = kTmemA ? chain_carve(smem, kOffAct + kDgSlots * 2 * kChunkBytes, SPARF_DG_RING, kOffBarBwd)
                               : chain_carve(smem, kOffEnc, kBwdStages, kOffBarBwd);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -1184,18 +1278,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           // index of the (tile, step, block) writes, slot = q & 1, k = q >> 1 its per-slot sequence number
           const uint32_t q = 34u * (uint32_t)it + (step == 0 ? (uint32_t)j : 2u + 4u * (uint32_t)(step - 1) + (uint32_t)j);
           const uint32_t n = j < 2 ? 9u * (uint32_t)it + (uint32_t)step : 8u * (uint32_t)it + (uint32_t)step - 1u;
-          const int bi = kTmemA ? (int)(q & 1u) : j;
+          const int bi = kTmemA ? (int)(q % (uint32_t)kDgSlots) : j;
           const uint8_t* src_hi = kTmemA ? smem + kOffAct + (size_t)bi * 2 * kChunkBytes : act_hi + (size_t)j * kChunkBytes;
           const uint8_t* src_lo = kTmemA ? src_hi + kChunkBytes : act_lo + (size_t)j * kChunkBytes;
-          mbar_wait(&cs.g_ready[bi], (kTmemA ? (q >> 1) : n) & 1);
+          mbar_wait(&cs.g_ready[bi], (kTmemA ? (q / (uint32_t)kDgSlots) : n) & 1);
           if (elect_one()) {
-            if (tile_ok) {
-              bulk_s2g(p.img.at(t_out, tile, j, 0), src_hi, kChunkBytes);
-              bulk_s2g(p.img.at(t_out, tile, j, 1), src_lo, kChunkBytes);
+            if (kTmemA) {
+              // (hi | lo) of a block are adjacent in the slot AND in the HBM image: one 32 KB bulk store.  A dummy tile
+              // (never with stand-alone CTAs) would still need its (empty) group for the in-flight accounting.
+              if (tile_ok) bulk_s2g(p.img.at(t_out, tile, j, 0), src_hi, 2 * kChunkBytes);
               bulk_commit_group();
-              bulk_wait_read_all();
+              bulk_wait_read<kStoreInflight - 1>();
+              if (q + 1u >= (uint32_t)kStoreInflight)
+                mbar_arrive(&cs.s_free[(q + 1u - (uint32_t)kStoreInflight) % (uint32_t)kDgSlots]);
+            } else {
+              if (tile_ok) {
+                bulk_s2g(p.img.at(t_out, tile, j, 0), src_hi, kChunkBytes);
+                bulk_s2g(p.img.at(t_out, tile, j, 1), src_lo, kChunkBytes);
+                bulk_commit_group();
+                bulk_wait_read_all();
+              }
+              mbar_arrive(&cs.s_free[bi]);
             }
-            mbar_arrive(&cs.s_free[bi]);
           }
           __syncwarp();
         }
@@ -1260,8 +1364,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           if (lane == 0) mbar_arrive(&cs.a_ready[j]);
         }
         if (kTmemA) {
-          const uint32_t q = 34u * (uint32_t)it + (uint32_t)j, k = q >> 1;
-          const int slot = (int)(q & 1u);
+          const uint32_t q = 34u * (uint32_t)it + (uint32_t)j, k = q / (uint32_t)kDgSlots;
+          const int slot = (int)(q % (uint32_t)kDgSlots);
           uint8_t* st_hi = smem + kOffAct + (size_t)slot * 2 * kChunkBytes;
           if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
           store16(sp, row, cq * kEpiCols, st_hi, st_hi + kChunkBytes);
@@ -1301,6 +1405,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         } else {
           tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
         }
+        if (kTmemA) {
+          // ---- phase 1 (critical path): mask -> bf16 (hi, lo) -> tensor memory, block by block: the MMA warp starts
+          // the next layer on K block j as soon as it is in.  The packed halves stay in registers for phase 2.
+          const bool chain = bl != kNumBwdLayers - 1;   // G0 is only saved, nothing consumes it on-chip
+          Split16 sps[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col0 = j * 64 + cq * kEpiCols;
+            float f[16];
+            const uint32_t mask = (masks[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float g = __uint_as_float(va[j][i]);
+              if (bl == 1) g = fmaf(g_raw, s_w7r0[col0 + i], g);   // density row joins the feature gradient
+              f[i] = ((mask >> i) & 1u) ? g : 0.f;
+            }
+            split16<false>(f, sps[j]);
+            if (chain) {
+              tmem_st8(tmem_base + t_lane + 256u + (uint32_t)(j * 32 + cq * 8), sps[j].hi);
+              tmem_st8(tmem_base + t_lane + 384u + (uint32_t)(j * 32 + cq * 8), sps[j].lo);
+              tmem_st_wait();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&cs.a_ready[j]);
+            }
+          }
+          // ---- phase 2 (overlaps the next layer's MMAs): the gradient image through the staging slots
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t q = 34u * (uint32_t)it + 2u + 4u * (uint32_t)bl + (uint32_t)j, k = q / (uint32_t)kDgSlots;
+            const int slot = (int)(q % (uint32_t)kDgSlots);
+            uint8_t* st_hi = smem + kOffAct + (size_t)slot * 2 * kChunkBytes;
+            long long tt3 = trace_tic();
+            if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
+            trace_toc(tr, 3, tt3);
+            store16(sps[j], row, cq * kEpiCols, st_hi, st_hi + kChunkBytes);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t v[16];
@@ -1337,8 +1482,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           }
           long long tt3 = trace_tic();
           if (kTmemA) {
-            const uint32_t q = 34u * (uint32_t)it + 2u + 4u * (uint32_t)bl + (uint32_t)j, k = q >> 1;
-            const int slot = (int)(q & 1u);
+            const uint32_t q = 34u * (uint32_t)it + 2u + 4u * (uint32_t)bl + (uint32_t)j, k = q / (uint32_t)kDgSlots;
+            const int slot = (int)(q % (uint32_t)kDgSlots);
             uint8_t* st_hi = smem + kOffAct + (size_t)slot * 2 * kChunkBytes;
             if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
             trace_toc(tr, 3, tt3);
@@ -1359,6 +1504,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             }
           }
         }
+        }   // (shared-memory-operand kernels)
         if (!kTmemA) {
           tc_fence_before();
           __syncwarp();
@@ -2036,16 +2182,17 @@ static int fwd_variant(bool f16, int passes, bool save, int num_tiles) {
 
 #ifdef SPARF_TC_TRACE
 static void trace_dump(const char* what) {
-  static long long h[148 * 4 * 8];
+  static long long h[148 * 6 * 8];
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h, g_tc_trace, sizeof(h));
-  const char* roles[4] = {"producer0 (w0 = ring slot free)", "mma issuer (w0 = acc free, w1 = A ready, w2 = weights landed)",
-                          "epilogue warp 0 (w0 = acc full, dgrad: w1 = mask loads, w2 = tmem ld, w3 = fence+arrive)", "epilogue warp 15"};
+  const char* roles[5] = {"producer0 (w0 = ring slot free)", "mma issuer (w0 = acc free, w1 = A ready, w2 = weights landed)",
+                          "epilogue warp 0 (w0 = acc full; fwd: w1 = staging slot free, w2 = tmem ld, w3 = encoding; dgrad: w1 = mask loads, w2 = tmem ld, w3 = staging slot free)",
+                          "epilogue warp 15", "image store warp (w0 = block staged, w1 = bulk store issue + source read)"};
   fprintf(stderr, "[tc trace] %s, mean over CTAs 0..147 (clocks)\n", what);
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < 5; ++r) {
     double a[5] = {0, 0, 0, 0, 0};
     for (int b = 0; b < 148; ++b)
-      for (int k = 0; k < 5; ++k) a[k] += (double)h[((size_t)b * 4 + r) * 8 + k] / 148.0;
+      for (int k = 0; k < 5; ++k) a[k] += (double)h[((size_t)b * 6 + r) * 8 + k] / 148.0;
     fprintf(stderr, "  %-70s total %9.0f  w0 %9.0f  w1 %9.0f  w2 %9.0f  w3 %9.0f\n", roles[r], a[4], a[0], a[1], a[2], a[3]);
   }
   if (getenv("SPARF_TC_TRACE_EVENTS")) {

@@ -253,6 +253,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt, int a_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same with different 16-bit formats for A and B (probe: does the hardware accept f16 x bf16 in one kind::f16 MMA?)
+__host__ __device__ constexpr uint32_t make_idesc_ab(int M, int N, int a_fmt, int b_fmt, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -110,8 +110,9 @@ __global__ void __launch_bounds__(128) selftest_gemm_kernel(const float* __restr
 //   D[128 (m), 128 (n)] = sum_{r < rows} G[r][m] * X[r][n],   G, X: [rows, 128] fp32 row-major, rows in {64, 128}
 // Both operands are written as the forward A-operand image ([rows x 64] blocks, sw128_offset(row, col)) and
 // consumed through MN-major descriptors.
+// x_fp16 != 0: X is stored as fp16 while G stays bf16 (mixed operand formats in one kind::f16 MMA)
 __global__ void __launch_bounds__(128) selftest_tn_kernel(const float* __restrict__ G, const float* __restrict__ X, int rows,
-                                                           float* __restrict__ D) {
+                                                           float* __restrict__ D, int x_fp16) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sG = smem;              // 2 feature blocks x 16 KB
@@ -137,9 +138,14 @@ __global__ void __launch_bounds__(128) selftest_tn_kernel(const float* __restric
         if (tid < rows) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(S[(size_t)tid * 128 + fb * 64 + c * 8 + 2 * e],
-                                                     S[(size_t)tid * 128 + fb * 64 + c * 8 + 2 * e + 1]);
-            w[e] = *reinterpret_cast<uint32_t*>(&h);
+            const float v0 = S[(size_t)tid * 128 + fb * 64 + c * 8 + 2 * e], v1 = S[(size_t)tid * 128 + fb * 64 + c * 8 + 2 * e + 1];
+            if (src == 1 && x_fp16) {
+              __half2 h = __floats2half2_rn(v0, v1);
+              w[e] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+              w[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
           }
         }
         *reinterpret_cast<uint4*>(dst + (size_t)fb * 16384 + sw128_offset(tid, c * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(128) selftest_tn_kernel(const float* __restric
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (tid == 0) {
-    const uint32_t idesc = make_idesc(128, 128, 1, 1, 1);
+    const uint32_t idesc = make_idesc_ab(128, 128, 1, x_fp16 ? 0 : 1, 1, 1);
     for (int ks = 0; ks < rows / 16; ++ks) {   // 16 sample rows = two 8-row atoms = 2048 bytes
       uint64_t da = make_smem_desc_mn(smem_u32(sG) + ks * 2048, 16384);
       uint64_t db = make_smem_desc_mn(smem_u32(sX) + ks * 2048, 16384);
@@ -182,7 +188,17 @@ extern "C" int sparf_tc_selftest_tn(const float* G, const float* X, int32_t rows
   SPARF_REQUIRE(rows == 64 || rows == 128, "tc_selftest_tn: rows=%d", rows);
   size_t smem = (size_t)4 * 16384 + 1024;
   SPARF_CHECK_CUDA(cudaFuncSetAttribute(selftest_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  selftest_tn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, X, rows, D);
+  selftest_tn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, X, rows, D, 0);
+  SPARF_CHECK_LAUNCH("selftest_tn_kernel");
+  return SPARF_OK;
+}
+
+// Probe: the same GEMM with G in bf16 and X in fp16 (a_format != b_format).  Debug entry (tools/probe_mixed_formats.py).
+extern "C" int sparf_tc_selftest_tn_mixed(const float* G, const float* X, int32_t rows, float* D, sparf_stream_t stream) {
+  SPARF_REQUIRE(rows == 64 || rows == 128, "tc_selftest_tn_mixed: rows=%d", rows);
+  size_t smem = (size_t)4 * 16384 + 1024;
+  SPARF_CHECK_CUDA(cudaFuncSetAttribute(selftest_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  selftest_tn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, X, rows, D, 1);
   SPARF_CHECK_LAUNCH("selftest_tn_kernel");
   return SPARF_OK;
 }

@@ -30,7 +30,9 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on the stream the warm-up ran on: autograd's AccumulateGrad nodes of leaf parameters (e.g. a pose
+        # embedding) are bound to the stream they were first used on
+        with torch.cuda.graph(self.graph, stream=side):
             self.outputs = fn(*self.static_inputs)
 
     def __call__(self, *inputs: torch.Tensor):
