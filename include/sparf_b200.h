@@ -17,6 +17,17 @@
  *     (thread-local).  No exceptions cross the ABI.
  *   - gradient outputs of *_backward are ACCUMULATED (+=) into the given buffers so that several
  *     render passes of one step can share one flat gradient buffer (the caller zeroes it once).
+ *
+ * Process-level state (all of it): the thread-local error string; a launch counter (sparf_launch_count); per device,
+ * lazily: the SM count, the kernels' shared-memory attributes, and ONE internal side stream + two events on which
+ * sparf_mlp_backward* runs its small CUDA-core reductions beside the weight-gradient kernel (fork after the dgrad
+ * chain, join before the call returns control of `stream`: callers see ordinary stream order, and the pattern is
+ * capturable into a CUDA graph).  A workspace must not be shared by calls running concurrently on different streams.
+ * Environment knobs, read once, for A/B timing only (defaults are the measured-fastest settings):
+ *   SPARF_TC_OVERLAP=0   no side stream (everything on `stream`)
+ *   SPARF_TC_TMEMA=0     chain kernels with shared-memory A operands (round-1 generation)
+ *   SPARF_TC_PAIRS=0|1   force the cta_group::2 CTA-pair chain kernels off / on
+ *   SPARF_TC_WCOPIES=n   replicas of the packed forward weight stream (L2 hot-spot experiment)
  */
 #ifndef SPARF_B200_H_
 #define SPARF_B200_H_

@@ -1405,47 +1405,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         } else {
           tmem_ld16(tmem_base + t_lane + (uint32_t)(buf * 256 + cq * kEpiCols), vn);
         }
-        if (kTmemA) {
-          // ---- phase 1 (critical path): mask -> bf16 (hi, lo) -> tensor memory, block by block: the MMA warp starts
-          // the next layer on K block j as soon as it is in.  The packed halves stay in registers for phase 2.
-          const bool chain = bl != kNumBwdLayers - 1;   // G0 is only saved, nothing consumes it on-chip
-          Split16 sps[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col0 = j * 64 + cq * kEpiCols;
-            float f[16];
-            const uint32_t mask = (masks[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float g = __uint_as_float(va[j][i]);
-              if (bl == 1) g = fmaf(g_raw, s_w7r0[col0 + i], g);   // density row joins the feature gradient
-              f[i] = ((mask >> i) & 1u) ? g : 0.f;
-            }
-            split16<false>(f, sps[j]);
-            if (chain) {
-              tmem_st8(tmem_base + t_lane + 256u + (uint32_t)(j * 32 + cq * 8), sps[j].hi);
-              tmem_st8(tmem_base + t_lane + 384u + (uint32_t)(j * 32 + cq * 8), sps[j].lo);
-              tmem_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&cs.a_ready[j]);
-            }
-          }
-          // ---- phase 2 (overlaps the next layer's MMAs): the gradient image through the staging slots
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t q = 34u * (uint32_t)it + 2u + 4u * (uint32_t)bl + (uint32_t)j, k = q / (uint32_t)kDgSlots;
-            const int slot = (int)(q % (uint32_t)kDgSlots);
-            uint8_t* st_hi = smem + kOffAct + (size_t)slot * 2 * kChunkBytes;
-            long long tt3 = trace_tic();
-            if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
-            trace_toc(tr, 3, tt3);
-            store16(sps[j], row, cq * kEpiCols, st_hi, st_hi + kChunkBytes);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
-          }
-        } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t v[16];
@@ -1504,7 +1463,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             }
           }
         }
-        }   // (shared-memory-operand kernels)
         if (!kTmemA) {
           tc_fence_before();
           __syncwarp();
@@ -2385,6 +2343,35 @@ int tc_mlp_backward_tape(const SparfMLP* mlp, int engine, int R, int S, const fl
                               workspace_bytes, reinterpret_cast<uint8_t*>(tape), sigma, rgb, st);
 }
 
+// Fork / join onto a library-owned side stream (one per device, created on first use): the CUDA-core leftovers of the
+// backward (bias / narrow-layer reductions, view-direction columns, ray gradients) only depend on the dgrad chain, so
+// they run BESIDE the HBM-bound weight-gradient kernel instead of after it (its CTAs leave ~30 KB of shared memory and
+// most thread slots of every SM free).  Event record / wait pairs make the pattern capturable into a CUDA graph.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+  static SideStream table[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideStream& s = table[dev & 63];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+  }
+  return &s;
+}
+static bool overlap_small_kernels() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPARF_TC_OVERLAP");     // 0: everything on the caller's stream (debugging / A-B timing)
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
                                 const float* t, const float* noise, const float* d_sigma, const float* d_rgb,
                                 const SparfMLPGrad* grad, float* d_origins, float* d_dirs, void* workspace,
@@ -2486,6 +2473,14 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 15, grad->trunk_b[l]);
     add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 14, nullptr);             // skip part of layer 4
     add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 14, grad->trunk_b[0]);          // layer 0 (+ its bias)
+    // fork: `sd` = the side stream (or the caller's stream when overlapping is off / unavailable)
+    SideStream* side = overlap_small_kernels() ? side_stream() : nullptr;
+    cudaStream_t sd = st;
+    if (side) {
+      SPARF_CHECK_CUDA(cudaEventRecord(side->fork, st));
+      SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      sd = side->stream;
+    }
     tc_mlp_wgrad_kernel<<<nj, 192, kWgSmem + 1024, st>>>(jobs_tab, img);
     SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
 
@@ -2504,34 +2499,38 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     // one launch per job shape (blockIdx.y = job index is passed through the first table entry of each launch)
     ReduceJobs one;
     one.j[0] = rj[0];
-    image_reduce_kernel<1><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, st>>>(one, img, Mc, ntiles, tpb);
+    image_reduce_kernel<1><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd>>>(one, img, Mc, ntiles, tpb);
     SPARF_CHECK_LAUNCH("image_reduce_kernel<1>");
     one.j[0] = rj[1];
-    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, st>>>(one, img, Mc, ntiles, tpb);
+    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd>>>(one, img, Mc, ntiles, tpb);
     SPARF_CHECK_LAUNCH("image_reduce_kernel<3>");
-    ray_sum_ghid_kernel<<<nr, 128, 0, st>>>(img, nr, S, c.rayS);
+    ray_sum_ghid_kernel<<<nr, 128, 0, sd>>>(img, nr, S, c.rayS);
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
-    ray_head_wgrad_kernel<<<ceil_div(nr, 8), 128, 0, st>>>(nr, 8, c.rayS, c.denc, grad->head_w[0]);
+    ray_head_wgrad_kernel<<<ceil_div(nr, 8), 128, 0, sd>>>(nr, 8, c.rayS, c.denc, grad->head_w[0]);
     SPARF_CHECK_LAUNCH("ray_head_wgrad_kernel");
 
     // 5. gradients w.r.t. the rays (camera-pose optimisation)
     if (d_origins != nullptr || d_dirs != nullptr) {
-      pack_weights_enc_kernel<<<16, 256, 0, st>>>(mlp->trunk_w[4], mlp->trunk_w[0], c.packed_e);
+      pack_weights_enc_kernel<<<16, 256, 0, sd>>>(mlp->trunk_w[4], mlp->trunk_w[0], c.packed_e);
       SPARF_CHECK_LAUNCH("pack_weights_enc_kernel");
       EncGradParams ep;
       ep.packed = c.packed_e; ep.img = img; ep.t = t + m0;
       ep.d_origins = d_origins ? d_origins + (size_t)r0 * 3 : nullptr;
       ep.d_dirs = d_dirs ? d_dirs + (size_t)r0 * 3 : nullptr;
       ep.M = Mc; ep.S = S; ep.num_tiles = ntiles;
-      tc_mlp_encgrad_kernel<<<std::min(ntiles, num_sms()), 192, kEgSmem + 1024, st>>>(ep);
+      tc_mlp_encgrad_kernel<<<std::min(ntiles, num_sms()), 192, kEgSmem + 1024, sd>>>(ep);
       SPARF_CHECK_LAUNCH("tc_mlp_encgrad_kernel");
       if (d_dirs) {
-        ray_head_dgrad_kernel<<<ceil_div(nr * 32, 256), 256, 0, st>>>(nr, c.rayS, mlp->head_w[0], c.gdenc);
+        ray_head_dgrad_kernel<<<ceil_div(nr * 32, 256), 256, 0, sd>>>(nr, c.rayS, mlp->head_w[0], c.gdenc);
         SPARF_CHECK_LAUNCH("ray_head_dgrad_kernel");
-        direnc_bwd_kernel<<<ceil_div(nr, 128), 128, 0, st>>>(nr, kLv, 32, c.denc, c.gdenc, dirs + (size_t)r0 * 3,
+        direnc_bwd_kernel<<<ceil_div(nr, 128), 128, 0, sd>>>(nr, kLv, 32, c.denc, c.gdenc, dirs + (size_t)r0 * 3,
                                                              d_dirs + (size_t)r0 * 3);
         SPARF_CHECK_LAUNCH("direnc_bwd_kernel");
       }
+    }
+    if (side) {   // join: later work on the caller's stream (next chunk, optimiser, ...) sees every gradient
+      SPARF_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+      SPARF_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     }
   }
   return SPARF_OK;

@@ -221,8 +221,14 @@ class Graph(torch.nn.Module):
         if opt.nerf.fine_sampling and not self._fine_disabled(opt, iter):
             keys += [k + "_fine" for k in keys]
         ret_all = edict({k: [] for k in keys})
-        for c in range(0, H * W, opt.nerf.rand_rays):
-            ray_idx = torch.arange(c, min(c + opt.nerf.rand_rays, H * W), device=self.device)
+        step = opt.nerf.rand_rays
+        if mode in ["val", "eval", "test"] or not (opt.nerf.sample_stratified or opt.nerf.density_noise_reg):
+            # Nothing random is drawn in these modes (renderer.py:326, 404; frequency_nerf.py:191) and rays do not
+            # interact, so the slice size does not change any output: use slices as large as comfortably fit, i.e. one
+            # persistent forward-only kernel launch over (up to) 131072 rays instead of H*W / rand_rays small ones.
+            step = max(step, self.full_image_rays_per_launch // max(1, len(pose)))
+        for c in range(0, H * W, step):
+            ray_idx = torch.arange(c, min(c + step, H * W), device=self.device)
             ret = self.render(opt, pose, H=H, W=W, intr=intr, ray_idx=ray_idx, depth_range=depth_range, iter=iter, mode=mode)
             for k in ret_all:
                 if k in ret.keys():
@@ -248,6 +254,8 @@ class Graph(torch.nn.Module):
     # copy per step).  device_side_rng = True -- and always while a CUDA graph is being captured, where a pageable
     # host copy cannot be recorded -- draws the same U[0,1) grid with the device generator instead.
     device_side_rng = False
+    # render_by_slices in the deterministic modes: rays (over all views) per forward launch
+    full_image_rays_per_launch = 131072
 
     def _shared_grid_midpoints(self, n_samples_fine, det):
         # renderer.py:435-442: one grid for all rays
