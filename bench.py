@@ -58,7 +58,7 @@ CONFIGS = {
                desc="DTU-shaped joint pose-NeRF (BARF c2f mask + 9-D pose embeddings with gradients), 1023 rays, hierarchical 128 + 256 samples, photometric loss, fwd+bwd"),
     "c4": dict(B=3, H=378, W=504, focal=500.0, rand_rays=2048, S=128, fine=False, S_fine=128, depth_range=(1, 0),
                data_depth_range=(0.5, 8.0), depth_param="inverse", poses=True, c2f=(0.4, 0.7), progress=0.55,
-               loss_type="photometric_and_corres_and_depth_cons", scaling="weak", graph=False,
+               loss_type="photometric_and_corres_and_depth_cons", scaling="weak",
                desc="LLFF-shaped 3 views 378x504, joint poses, 3x682=2046 rays x 128 inverse-depth samples, full SPARF step: photometric + correspondence + depth-consistency (6 render calls), fwd+bwd"),
     "c5": dict(B=9, H=340, W=600, focal=600.0, rand_rays=4096, S=128, fine=True, S_fine=128, depth_range=(0.1, 4.5),
                depth_param="metric", poses=True, c2f=(0.4, 0.7), progress=0.55, loss_type="photometric", scaling="strong",
@@ -192,7 +192,10 @@ def build_problem(cfg_name, impl, device, seed=0, stratified=True):
         net.nerf_fine.load_state_dict(sd_fine)
     net.to(device).train()
     flow = common.FakeFlowNet(B, H, W) if "corres" in cfg["loss_type"] else None
-    loss_module = define_loss(opt.loss_type, opt, net, _TrainData(data, B), device, flow_net=flow)
+    if impl == "ours":   # sync-free fixed-shape mode of the SPARF losses: the step is one CUDA graph
+        loss_module = define_loss(opt.loss_type, opt, net, _TrainData(data, B), device, flow_net=flow, device_side=True)
+    else:
+        loss_module = define_loss(opt.loss_type, opt, net, _TrainData(data, B), device, flow_net=flow)
     modules = [net] + ([pose_net] if pose_net is not None else [])
     pr = argparse.Namespace(cfg=cfg, opt=opt, data=data, net=net, pose_net=pose_net, loss_module=loss_module,
                             modules=modules, iteration=10)

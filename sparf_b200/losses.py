@@ -53,7 +53,7 @@ def pose_inverse_4x4(mat: torch.Tensor) -> torch.Tensor:
 
 def batch_backproject_to_3d(kpi, di, Ki, T_itoj):
     """pixels [N,2] with depth [N] -> 3-D points in frame j [N,3]."""
-    x = to_homogeneous(kpi) @ torch.inverse(Ki).transpose(-1, -2)
+    x = to_homogeneous(kpi) @ torch.linalg.inv_ex(Ki).inverse.transpose(-1, -2)   # (inv_ex: no host-side singularity check)
     x = x * di[..., None]
     return from_homogeneous(to_homogeneous(x) @ T_itoj.transpose(-1, -2))
 
@@ -93,27 +93,7 @@ def get_nearest_pose_ids(tar_pose_c2w: np.ndarray, ref_poses_c2w: np.ndarray, ta
     return int(np.argsort(d)[0])
 
 
-def sample_rays(H: int, W: int, nbr: int = None, fraction_in_center: float = 0.0, precrop_frac: float = 0.5):
-    """Random pixels of the (H-1)x(W-1) grid as float [N,2] (+ flat indices), sampling_strategies.py:250-295."""
-    ys, xs = torch.meshgrid(torch.arange(H - 1), torch.arange(W - 1), indexing="ij")
-    x_ind, y_ind = xs.reshape(-1), ys.reshape(-1)
-    if fraction_in_center > 0.0:
-        dH, dW = int(H // 2 * precrop_frac), int(W // 2 * precrop_frac)
-        Yc, Xc = torch.meshgrid(torch.linspace(H // 2 - dH, H // 2 + dH - 1, 2 * dH),
-                                torch.linspace(W // 2 - dW, W // 2 + dW - 1, 2 * dW), indexing="ij")
-        center = torch.stack([Xc, Yc], -1).view(-1, 2)
-        if nbr is not None:
-            n_c = int(nbr * fraction_in_center)
-            idx = torch.randperm(len(x_ind), device=x_ind.device)[:nbr - n_c]
-            x_ind, y_ind = x_ind[idx], y_ind[idx]
-            idx = torch.randperm(len(center), device=x_ind.device)[:n_c]
-            x_ind = torch.cat((x_ind, center[idx][..., 0]))
-            y_ind = torch.cat((y_ind, center[idx][..., 1]))
-    elif nbr is not None:
-        idx = torch.randperm(len(x_ind), device=x_ind.device)[:nbr]
-        x_ind, y_ind = x_ind[idx], y_ind[idx]
-    px = torch.stack([x_ind, y_ind], dim=-1).reshape(len(x_ind), -1)
-    return px.float(), px[..., 1] * W + px[..., 0]
+from .sampling_strategies import sample_rays  # noqa: E402,F401  (sampling_strategies.py:250-295)
 
 
 def _with_defaults(defaults: Dict[str, Any], opt) -> edict:
@@ -331,6 +311,14 @@ class CorrespondencesPairRenderDepthAndGet3DPtsAndReproject(BaseLoss):
                     renderrepro_pixel_reprojection_thresh=10.0, renderrepro_depth_reprojection_thresh=0.1,
                     use_gt_depth=False, use_gt_correspondences=False, use_dummy_all_one_confidence=False)
 
+    # device_side = True: the per-step work takes NO host decision and has fixed shapes, so a whole SPARF
+    # step is sync-free and capturable into one CUDA graph: the image pair is drawn with the device generator, the
+    # valid correspondences are sub-sampled by a top-k over random keys (a uniformly random subset of the valid set,
+    # like the reference's randperm) into a fixed-capacity buffer of rand_rays // 2 points + a validity mask, and the
+    # loss normalises by the device-side count.  The random stream differs from the reference's; the arithmetic per
+    # selected point does not (tests/test_losses.py checks both modes against each other with injected choices).
+    device_side = False
+
     def __init__(self, opt, nerf_net, flow_net, train_data, device):
         super().__init__(device)
         self.opt = _with_defaults(self.DEFAULTS, opt)
@@ -386,11 +374,62 @@ class CorrespondencesPairRenderDepthAndGet3DPtsAndReproject(BaseLoss):
             loss_dict["corres"] = loss_dict["corres"] / gamma
         return loss_dict, stats, plots
 
+    # ---- device-side mode -------------------------------------------------------------------------------------
+    def _rand_pair(self):
+        """index into filtered_flow_pairs as a [1] device tensor"""
+        return torch.randint(len(self.filtered_flow_pairs), (1,), device=self.device)
+
+    def _rand_keys(self, n):
+        return torch.rand(n, device=self.device)
+
+    def _device_tables(self):
+        if not hasattr(self, "_pair_tab"):
+            tab = torch.tensor([[i, a, b] for i, a, b in self.filtered_flow_pairs], dtype=torch.long, device=self.device)
+            self._pair_tab = tab.reshape(-1, 3)
+            self._grid_px = self.grid.reshape(-1, 2)
+        return self._pair_tab
+
+    def _compute_loss_pairwise_device(self, opt, data_dict, iteration):
+        B, _, H, W = data_dict.image.shape
+        tab = self._device_tables()
+        row = tab.index_select(0, self._rand_pair())[0]
+        i_map, id_self, id_other = row[0:1], row[1:2], row[2:3]
+        corres = self.corres_maps.index_select(0, i_map)[0].permute(1, 2, 0)[:, :, :2].reshape(-1, 2).detach()
+        conf = self.conf_maps.index_select(0, i_map)[0].permute(1, 2, 0).reshape(-1, 1).detach()
+        mask = self.mask_valid_corr.index_select(0, i_map)[0, 0]
+        if iteration < self.opt.precrop_iters:
+            dH, dW = int(H // 2 * self.opt.precrop_frac), int(W // 2 * self.opt.precrop_frac)
+            center = torch.zeros_like(mask)
+            center[H // 2 - dH:H // 2 + dH - 1, W // 2 - dW:W // 2 + dW - 1] = 1
+            mask = mask & center
+        mask = mask.reshape(-1)
+        enough = (mask.sum() >= self.opt.min_nbr_matches).float()        # corres_loss / base_corres_loss early return
+        n = min(self.opt.nerf.rand_rays // 2, H * W)
+        keys = torch.where(mask, self._rand_keys(H * W), torch.full((), 2.0, device=self.device))
+        val, idx = torch.topk(keys, n, largest=False)                    # random subset of the valid pixels, padded
+        valid = (val < 1.5)[:, None]                                     # [n,1]
+        px_self = self._grid_px.index_select(0, idx)
+        px_other = torch.where(valid, corres.index_select(0, idx), px_self)   # padding: any finite in-image pixel
+        conf_v = conf.index_select(0, idx)
+        poses = data_dict.poses_w2c
+        bottom = torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=poses.device)
+        P_self = torch.cat((poses.index_select(0, id_self)[0], bottom), 0)
+        P_other = torch.cat((poses.index_select(0, id_other)[0], bottom), 0)
+        K_self, K_other = data_dict.intr.index_select(0, id_self)[0], data_dict.intr.index_select(0, id_other)[0]
+        loss_dict, stats, _ = self.compute_loss_on_image_pair(data_dict, P_self, P_other, K_self, K_other, None, None, None,
+                                                              {"render_matches": torch.zeros((), device=self.device)}, {}, {},
+                                                              selected=(px_self, px_other, conf_v, valid))
+        loss_dict["corres"] = loss_dict["corres"] * enough
+        stats["perc_valid_corr_mask"] = mask.sum() / (mask.nelement() + 1e-6)
+        return loss_dict, stats, {}
+
     def compute_loss_pairwise(self, opt, data_dict, output_dict, iteration, mode=None, plot=False):
-        loss_dict = {"corres": torch.tensor(0.0, requires_grad=True).to(self.device),
-                     "render_matches": torch.tensor(0.0, requires_grad=True).to(self.device)}
+        loss_dict = {"corres": torch.zeros((), device=self.device, requires_grad=True),
+                     "render_matches": torch.zeros((), device=self.device, requires_grad=True)}
         if mode != "train" or iteration < self.opt.start_iter.corres or len(self.filtered_flow_pairs) == 0:
             return loss_dict, {}, {}
+        if self.device_side:
+            return self._compute_loss_pairwise_device(opt, data_dict, iteration)
         id_self, id_other, corres_map, conf_map, _, mask = self.sample_valid_image_pair()
         if iteration < self.opt.precrop_iters:
             H, W = data_dict.image.shape[-2:]
@@ -420,11 +459,11 @@ class CorrespondencesPairRenderDepthAndGet3DPtsAndReproject(BaseLoss):
                                                data_dict.intr[id_matching_view], corres, conf, mask, loss_dict,
                                                stats_dict, plotting_dict)
 
-    def _reprojection(self, px_i, depth_i, K_i, px_j, depth_j, K_j, T_i2j, conf, stats):
+    def _reprojection(self, px_i, depth_i, K_i, px_j, depth_j, K_j, T_i2j, conf, stats, valid0=None):
         """compute_render_and_repro_loss_w_repro_thres (corres_loss.py:50-95)."""
         proj, depth_proj = batch_project_to_other_img(px_i.float(), depth_i, K_i, K_j, T_i2j, return_depth=True)
         err = torch.norm(proj - px_j, dim=-1, keepdim=True)
-        valid = torch.ones_like(err).bool()
+        valid = torch.ones_like(err).bool() if valid0 is None else valid0
         if self.opt.renderrepro_do_pixel_reprojection_check:
             ok = err.detach().le(self.opt.renderrepro_pixel_reprojection_thresh)
             valid = valid & ok
@@ -436,16 +475,20 @@ class CorrespondencesPairRenderDepthAndGet3DPtsAndReproject(BaseLoss):
         return self.compute_diff_loss(self.opt.diff_loss_type, proj - px_j, weights=conf, mask=valid, dim=-1)
 
     def compute_loss_on_image_pair(self, data_dict, P_self, P_other, K_self, K_other, corres, conf, mask, loss_dict,
-                                   stats_dict, plotting_dict):
+                                   stats_dict, plotting_dict, selected=None):
         iteration = data_dict["iter"]
         H, W = data_dict.image.shape[-2:]
-        px_self = self.grid[mask]
-        px_other = corres[mask]
-        conf_v = conf[mask]
-        half = self.opt.nerf.rand_rays // 2
-        if px_self.shape[0] > half:                                      # corres_loss.py:149-157
-            sel = torch.randperm(px_self.shape[0], device=self.device)[:half].to(px_self.device)
-            px_self, px_other, conf_v = px_self[sel], px_other[sel], conf_v[sel]
+        valid0 = None
+        if selected is not None:             # device-side mode: fixed-capacity selection + validity mask
+            px_self, px_other, conf_v, valid0 = selected
+        else:
+            px_self = self.grid[mask]
+            px_other = corres[mask]
+            conf_v = conf[mask]
+            half = self.opt.nerf.rand_rays // 2
+            if px_self.shape[0] > half:                                      # corres_loss.py:149-157
+                sel = torch.randperm(px_self.shape[0], device=self.device)[:half].to(px_self.device)
+                px_self, px_other, conf_v = px_self[sel], px_other[sel], conf_v[sel]
         ret_self = self.net.render_image_at_specific_pose_and_rays(self.opt, data_dict, P_self[:3], K_self, H, W,
                                                                    pixels=px_self, mode="train", iter=iteration)
         ret_other = self.net.render_image_at_specific_pose_and_rays(self.opt, data_dict, P_other[:3], K_other, H, W,
@@ -459,8 +502,8 @@ class CorrespondencesPairRenderDepthAndGet3DPtsAndReproject(BaseLoss):
         total = 0.0
         for k in keys:
             d_s, d_o = ret_self[k].squeeze(0).squeeze(-1), ret_other[k].squeeze(0).squeeze(-1)
-            total = total + self._reprojection(px_self, d_s, K_self, px_other, d_o, K_other, T_s2o, conf_v, stats_dict)
-            total = total + self._reprojection(px_other, d_o, K_other, px_self, d_s, K_self, T_o2s, conf_v, stats_dict)
+            total = total + self._reprojection(px_self, d_s, K_self, px_other, d_o, K_other, T_s2o, conf_v, stats_dict, valid0)
+            total = total + self._reprojection(px_other, d_o, K_other, px_self, d_s, K_self, T_o2s, conf_v, stats_dict, valid0)
         loss_dict["corres"] = total / (2.0 * len(keys))
         return loss_dict, stats_dict, plotting_dict
 
@@ -475,10 +518,82 @@ class DepthConsistencyLoss(BaseLoss):
     DEFAULTS = dict(gradually_decrease_geo_sampling_loss=False, geo_sampling_loss_reduct_at_x_iter=10000,
                     diff_loss_type="huber")
 
+    # device_side = True: no host decision, fixed shapes (see the correspondence loss): the reference view, the
+    # interpolation weight and the pixels are drawn with the device generator, the nearest camera is an argmin on the
+    # device, and the two data-dependent filters (inside the virtual image & in front of the near plane; visibility
+    # >= 0.2) become a validity mask over ALL sampled points (invalid ones are moved to a safe dummy point, rendered and
+    # weighted 0); the mean divides by the device-side count of valid points.
+    device_side = False
+
     def __init__(self, opt, nerf_net, device):
         super().__init__(device)
         self.opt = _with_defaults(self.DEFAULTS, opt)
         self.net = nerf_net
+
+    # ---- device-side mode -------------------------------------------------------------------------------------
+    def _rand_image(self, B):
+        return torch.randint(B, (1,), device=self.device)
+
+    def _rand_weight(self):
+        return torch.rand((), device=self.device)
+
+    def _rand_pixels(self, H, W, n):
+        return sample_rays(H, W, nbr=n, fraction_in_center=self.opt.sampled_fraction_in_center, device=self.device)[0]
+
+    def _compute_loss_device(self, opt, data_dict, iteration):
+        B, _, H, W = data_dict.image.shape
+        bottom = torch.tensor([0, 0, 0, 1], device=self.device).reshape(1, 1, -1).repeat(B, 1, 1)
+        poses_w2c = torch.cat((data_dict.poses_w2c.detach(), bottom.to(data_dict.poses_w2c.dtype)), dim=1)
+        poses_c2w = pose_inverse_4x4(poses_w2c)
+        id_self = self._rand_image(B)
+        px_ref = self._rand_pixels(H, W, max(1024, self.opt.nerf.rand_rays)).reshape(-1, 2)
+        K_ref, P_ref = data_dict.intr.index_select(0, id_self)[0], poses_w2c.index_select(0, id_self)[0]
+        ret_ref = self.net.render_image_at_specific_pose_and_rays(self.opt, data_dict, pose=P_ref[:3], intr=K_ref, H=H, W=W,
+                                                                  pixels=px_ref, mode="train", iter=iteration)
+        use_fine = "depth_fine" in ret_ref.keys()
+        if use_fine and hasattr(opt.nerf, "ratio_start_fine_sampling_at_x") and opt.nerf.ratio_start_fine_sampling_at_x is not None \
+                and iteration < opt.max_iter * (opt.nerf.ratio_start_fine_sampling_at_x + 0.05):
+            use_fine = False
+        depth_ref = (ret_ref.depth_fine if use_fine else ret_ref.depth).squeeze(0).squeeze(-1)
+        c2w_self = poses_c2w.index_select(0, id_self)[0]
+        pts_w = batch_backproject_to_3d(px_ref, depth_ref, K_ref, c2w_self)
+        # nearest other camera by the angle between camera-position vectors (data_utils.py:267-311), on the device
+        pos = poses_c2w[:, :3, 3]
+        unit = pos / (pos.norm(dim=1, keepdim=True) + 1e-6)
+        ang = torch.acos((unit * unit.index_select(0, id_self)).sum(-1).clamp(-1.0, 1.0))
+        ang = ang.scatter(0, id_self, torch.full((1,), 1e3, device=self.device))
+        id_other = torch.argmin(ang, dim=0, keepdim=True)
+        w = self._rand_weight()
+        unseen_c2w = w * c2w_self.detach() + (1 - w) * poses_c2w.index_select(0, id_other)[0].detach()
+        P_unseen = pose_inverse_4x4(unseen_c2w)
+        K = K_ref.clone()
+        near = data_dict.depth_range[0][0]
+        with torch.no_grad():
+            px0, z0 = batch_project(pts_w, P_unseen, K, return_depth=True)
+            ok = px0[:, 0].ge(0.0) & px0[:, 1].ge(0.0) & px0[:, 0].le(W - 1) & px0[:, 1].le(H - 1) & z0.ge(near)
+            # a dummy world point for the rejected ones: on the virtual camera's axis, one unit behind the near plane
+            safe = (unseen_c2w[:3, :3] @ torch.stack([torch.zeros_like(near), torch.zeros_like(near), near + 1.0]) + unseen_c2w[:3, 3])
+        pts_s = torch.where(ok[:, None], pts_w, safe[None].expand_as(pts_w))
+        px, z = batch_project(pts_s, P_unseen, K, return_depth=True)      # finite everywhere, grad only through valid points
+        with torch.no_grad():
+            vis_ret = self.net.render_up_to_maxdepth_at_specific_pose_and_rays(
+                self.opt, data_dict, P_unseen[:3], K, H, W, depth_max=z, pixels=px, mode="train", iter=iteration)
+            key = "all_cumulated_fine" if "all_cumulated_fine" in vis_ret.keys() else "all_cumulated"
+            vis = vis_ret[key].squeeze(0).unsqueeze(-1)
+        valid = ok & vis.ge(0.2).reshape(-1)
+        ret = self.net.render_image_at_specific_pose_and_rays(self.opt, data_dict, P_unseen[:3], K, H, W, pixels=px,
+                                                              mode="train", iter=iteration)
+        total = 0.0
+        for suf in [""] + (["_fine"] if "rgb_fine" in ret.keys() else []):
+            depth = ret["depth" + suf].squeeze().reshape(-1)
+            wgt = vis * ret["opacity" + suf].squeeze(0).detach()
+            total = total + self.compute_diff_loss(self.opt.diff_loss_type, diff=z.view(-1) - depth.view(-1), weights=wgt.view(-1),
+                                                   mask=valid)
+        stats = {"nbr_px_sampling": valid.sum(), "avg_vis_weight": (wgt.view(-1) * valid).sum() / (valid.sum() + 1e-6)}
+        loss = {"depth_cons": total}
+        if self.opt.gradually_decrease_depth_cons_loss:
+            loss["depth_cons"] = loss["depth_cons"] / (2 ** (iteration // self.opt.depth_cons_loss_reduct_at_x_iter))
+        return loss, stats, {}
 
     def sample_pose(self, poses_c2w, id_self, pose_w2c_self):
         """w * own + (1-w) * nearest other camera, on the 4x4 matrices (depth_cons_loss.py:45-63).  The
@@ -496,6 +611,8 @@ class DepthConsistencyLoss(BaseLoss):
     def compute_loss(self, opt, data_dict, output_dict, iteration, mode=None, plot=False, **kwargs):
         if mode != "train" or iteration < self._start_iter(opt):
             return {}, {}, {}
+        if self.device_side:
+            return self._compute_loss_device(opt, data_dict, iteration)
         B, _, H, W = data_dict.image.shape
         bottom = torch.tensor([0, 0, 0, 1], device=self.device).reshape(1, 1, -1).repeat(B, 1, 1)
         poses_w2c = torch.cat((data_dict.poses_w2c.detach(), bottom.to(data_dict.poses_w2c.dtype)), dim=1)
@@ -591,8 +708,9 @@ class SparseCOLMAPDepthLoss(BaseLoss):
         return edict(colmap_depth=0.1 * total / B), stats, {}      # DS-NeRF's weighting
 
 
-def define_loss(loss_type: str, opt, nerf_net, train_data, device, flow_net=None) -> Loss:
-    """loss_factory.py:25-42."""
+def define_loss(loss_type: str, opt, nerf_net, train_data, device, flow_net=None, device_side: bool = False) -> Loss:
+    """loss_factory.py:25-42.  device_side=True switches the correspondence / depth-consistency modules to their
+    sync-free fixed-shape mode and drops the per-key host asserts of the aggregator (one CUDA graph per SPARF step)."""
     mods = []
     if "photometric" in loss_type:
         mods.append(BasePhotoandReguLoss(opt, nerf_net, train_data=train_data, device=device))
@@ -603,4 +721,10 @@ def define_loss(loss_type: str, opt, nerf_net, train_data, device, flow_net=None
                                                                           train_data=train_data, device=device))
     if "depth_cons" in loss_type:
         mods.append(DepthConsistencyLoss(opt, nerf_net, device=device))
-    return Loss(mods)
+    agg = Loss(mods)
+    if device_side:
+        agg.check_finite = False
+        for m in mods:
+            if hasattr(m, "device_side"):
+                m.device_side = True
+    return agg

@@ -375,6 +375,8 @@ def cached(tag: str, tensor: torch.Tensor, fn):
     by storage address + in-place version, so that the hot loop neither recomputes it nor synchronises."""
     key = (tag, tensor.data_ptr(), tensor._version, tuple(tensor.shape), tensor.device)
     hit = _HOST_CACHE.get(key)
+    if hit is None and tensor.is_cuda and torch.cuda.is_current_stream_capturing():
+        return fn(tensor)          # graph-pool temporaries must not be memoised (their addresses are recycled)
     if hit is None:
         if len(_HOST_CACHE) > 256:
             _HOST_CACHE.clear()
@@ -388,7 +390,8 @@ def raygen(pose_w2c, intr, W: int, *, ray_idx=None, pixels=None):
     """pose_w2c [B,3,4], intr [B,3,3] -> (center, ray) [B,n,3] at ray_idx ((n,)/(B,n) int) or float pixels."""
     assert (ray_idx is None) != (pixels is None)
     # camera.py:318-319; intrinsics carry no gradient and are constant over training: invert once
-    intr_inv = cached("Kinv", intr, lambda k: torch.linalg.inv(k.detach().float()))
+    # (inv_ex: no host-side singularity check, i.e. no synchronisation)
+    intr_inv = cached("Kinv", intr, lambda k: torch.linalg.inv_ex(k.detach().float()).inverse)
     return RayGenFunction.apply(pose_w2c, intr_inv, W, ray_idx, pixels)
 
 

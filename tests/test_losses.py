@@ -178,3 +178,137 @@ def test_reference_trainer_graph_and_losses_on_our_renderer(name):
                        ray_idx, net, loss_module, pose_net.pose_embedding, gtol=6e-2)
     finally:
         ref_loader._purge()
+
+
+def _sparf_problem(dev, stratified):
+    import sparf_b200
+    from sparf_b200.poses_models import FirstTwoColunmnsPoseParameters
+    from sparf_b200.renderer import Graph
+    sparf_b200.set_engine("auto")
+    gold, c, opt, data, ray_idx, sd, sd_fine, init_w2c = _loss_case_setup("c7_sparf_losses", dev)
+    opt.nerf.sample_stratified = stratified
+    pose_net = FirstTwoColunmnsPoseParameters(opt, nbr_poses=c["B"], initial_poses_w2c=init_w2c, device=dev).to(dev)
+
+    class PoseGraph(Graph):
+        def get_w2c_pose(self, opt, data_dict, mode=None):
+            return pose_net.get_w2c_poses()
+
+    net = PoseGraph(opt, dev)
+    net.nerf.load_state_dict(sd)
+    net.nerf_fine.load_state_dict(sd_fine)
+    net.to(dev).train()
+    return c, opt, data, ray_idx, net, pose_net
+
+
+def _sparf_step(c, opt, data, ray_idx, net, loss_module):
+    data["iter"] = c["iteration"]
+    out = net.render_image_at_specific_rays(opt, data, iter=c["iteration"], ray_idx=ray_idx, mode="train")
+    data.poses_w2c = net.get_w2c_pose(opt, data, mode="train")
+    loss_dict, stats, _ = loss_module.compute_loss(opt, data, out, iteration=c["iteration"], mode="train")
+    loss_dict["all"].backward()
+    data.pop("poses_w2c", None)
+    return loss_dict
+
+
+@pytest.mark.gpu
+def test_device_side_losses_match_host_mode():
+    """the sync-free fixed-capacity mode of the correspondence / depth-consistency losses computes the same
+    losses and gradients as the reference-faithful mode when both are given the same random choices (deterministic depth
+    sampling so that padding rays do not shift any random stream)."""
+    from sparf_b200.losses import define_loss
+    dev = torch.device("cuda")
+    rec = {"randint": [], "rand": [], "perm": []}
+    results = {}
+    for mode in ("host", "device"):
+        c, opt, data, ray_idx, net, pose_net = _sparf_problem(dev, stratified=False)
+        flow = common.FakeFlowNet(c["B"], c["H"], c["W"])
+        loss_module = define_loss(opt.loss_type, opt, net, _TrainData(data, c["B"]), dev, flow_net=flow, device_side=(mode == "device"))
+        corres_mod, dc_mod = loss_module.loss_modules[1], loss_module.loss_modules[2]
+        if mode == "host":      # spy on the reference-order draws
+            o_randint, o_rand, o_perm = np.random.randint, np.random.rand, torch.randperm
+            np.random.seed(11)
+            torch.manual_seed(11)
+
+            def spy_randint(*a, **k):
+                v = o_randint(*a, **k); rec["randint"].append(int(v)); return v
+
+            def spy_rand(*a, **k):
+                v = o_rand(*a, **k); rec["rand"].append(float(v)); return v
+
+            def spy_perm(*a, **k):
+                v = o_perm(*a, **k); rec["perm"].append(v.detach().cpu().clone()); return v
+
+            np.random.randint, np.random.rand, torch.randperm = spy_randint, spy_rand, spy_perm
+            try:
+                losses = _sparf_step(c, opt, data, ray_idx, net, loss_module)
+            finally:
+                np.random.randint, np.random.rand, torch.randperm = o_randint, o_rand, o_perm
+            assert len(rec["randint"]) == 2 and len(rec["rand"]) == 1 and len(rec["perm"]) == 2
+        else:                   # replay them through the device-side hooks
+            k_pair, id_self = rec["randint"]
+            perm_corres, perm_px = rec["perm"]
+            H, W = c["H"], c["W"]
+            half = opt.nerf.rand_rays // 2
+            i_map = corres_mod.filtered_flow_pairs[k_pair][0]
+            valid_idx = corres_mod.mask_valid_corr[i_map, 0].reshape(-1).nonzero()[:, 0]
+            keys = torch.full((H * W,), 1.0, device=dev)
+            sel = valid_idx[perm_corres[:half].to(dev)]
+            keys[sel] = torch.arange(len(sel), device=dev, dtype=torch.float32) / (2.0 * len(sel))
+            corres_mod._rand_pair = lambda: torch.tensor([k_pair], device=dev)
+            corres_mod._rand_keys = lambda n: keys
+            from sparf_b200.sampling_strategies import sample_rays
+            ys, xs = torch.meshgrid(torch.arange(H - 1), torch.arange(W - 1), indexing="ij")
+            grid = torch.stack([xs.reshape(-1), ys.reshape(-1)], -1)
+            px = grid[perm_px[: max(1024, opt.nerf.rand_rays)]].float().to(dev)
+            dc_mod._rand_image = lambda B: torch.tensor([id_self], device=dev)
+            dc_mod._rand_weight = lambda: torch.tensor(rec["rand"][0], device=dev, dtype=torch.float32)
+            dc_mod._rand_pixels = lambda H_, W_, n: px
+            losses = _sparf_step(c, opt, data, ray_idx, net, loss_module)
+        torch.cuda.synchronize()
+        grads = [p.grad.detach().clone() for p in list(net.nerf.parameters()) + list(net.nerf_fine.parameters()) if p.grad is not None]
+        grads.append(pose_net.pose_embedding.grad.detach().clone())
+        results[mode] = ({k: float(v) for k, v in losses.items() if torch.is_tensor(v) and v.dim() == 0}, grads)
+    lh, gh = results["host"]
+    ld, gd = results["device"]
+    for k in ("render", "corres", "depth_cons", "all"):
+        assert abs(lh[k] - ld[k]) <= 2e-5 * max(abs(lh[k]), 1e-6), (k, lh[k], ld[k])
+    for a, b in zip(gh, gd):
+        assert (a - b).abs().max().item() <= 2e-4 * max(a.abs().max().item(), 1e-12)
+    print("device-side == host mode:", {k: "%.3e/%.3e" % (lh[k], ld[k]) for k in ("corres", "depth_cons")})
+
+
+@pytest.mark.gpu
+def test_sparf_step_is_sync_free_and_graph_capturable():
+    """A full SPARF step (photometric + correspondence + depth-consistency: 6 render calls, gradients to both networks
+    and the poses) in device-side mode performs NO host synchronisation (torch.cuda.set_sync_debug_mode('error')) and
+    replays as ONE CUDA graph."""
+    from sparf_b200.distributed import FlatGradients
+    from sparf_b200.graphs import GraphedStep
+    from sparf_b200.losses import define_loss
+    dev = torch.device("cuda")
+    c, opt, data, ray_idx, net, pose_net = _sparf_problem(dev, stratified=True)
+    net.device_side_rng = True
+    flow = common.FakeFlowNet(c["B"], c["H"], c["W"])
+    loss_module = define_loss(opt.loss_type, opt, net, _TrainData(data, c["B"]), dev, flow_net=flow, device_side=True)
+    fg = FlatGradients([net, pose_net])
+
+    def step(idx):
+        fg.zero_()
+        return _sparf_step(c, opt, data, idx, net, loss_module)["all"].detach()
+
+    step(ray_idx)                       # lazy initialisation (tables, workspaces, host caches) may synchronise
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        l1 = step(ray_idx)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert torch.isfinite(l1) and fg.flat.abs().sum() > 0
+    graphed = GraphedStep(step, (ray_idx.clone(),), warmup=2)
+    vals = []
+    for _ in range(3):
+        vals.append(float(graphed(ray_idx)))
+        assert torch.isfinite(fg.flat).all() and fg.flat.abs().sum() > 0
+    assert all(np.isfinite(v) for v in vals) and len(set(vals)) > 1     # fresh device-side random draws every replay
+    print("SPARF step as one CUDA graph:", vals)
