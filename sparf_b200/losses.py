@@ -96,6 +96,14 @@ def get_nearest_pose_ids(tar_pose_c2w: np.ndarray, ref_poses_c2w: np.ndarray, ta
 from .sampling_strategies import sample_rays  # noqa: E402,F401  (sampling_strategies.py:250-295)
 
 
+def _bottom_row(device, dtype=torch.float32) -> torch.Tensor:
+    """[0, 0, 0, 1] built ON the device (a python-list constructor is a pageable host->device copy: a synchronisation,
+    and illegal inside a CUDA-graph capture)."""
+    row = torch.zeros(4, device=device, dtype=dtype)
+    row[3] = 1
+    return row
+
+
 def _with_defaults(defaults: Dict[str, Any], opt) -> edict:
     out = edict(defaults)
     for k, v in opt.items():
@@ -412,7 +420,7 @@ class CorrespondencesPairRenderDepthAndGet3DPtsAndReproject(BaseLoss):
         px_other = torch.where(valid, corres.index_select(0, idx), px_self)   # padding: any finite in-image pixel
         conf_v = conf.index_select(0, idx)
         poses = data_dict.poses_w2c
-        bottom = torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=poses.device)
+        bottom = _bottom_row(poses.device)[None]
         P_self = torch.cat((poses.index_select(0, id_self)[0], bottom), 0)
         P_other = torch.cat((poses.index_select(0, id_other)[0], bottom), 0)
         K_self, K_other = data_dict.intr.index_select(0, id_self)[0], data_dict.intr.index_select(0, id_other)[0]
@@ -542,7 +550,7 @@ class DepthConsistencyLoss(BaseLoss):
 
     def _compute_loss_device(self, opt, data_dict, iteration):
         B, _, H, W = data_dict.image.shape
-        bottom = torch.tensor([0, 0, 0, 1], device=self.device).reshape(1, 1, -1).repeat(B, 1, 1)
+        bottom = _bottom_row(self.device).reshape(1, 1, -1).repeat(B, 1, 1)
         poses_w2c = torch.cat((data_dict.poses_w2c.detach(), bottom.to(data_dict.poses_w2c.dtype)), dim=1)
         poses_c2w = pose_inverse_4x4(poses_w2c)
         id_self = self._rand_image(B)

@@ -97,17 +97,23 @@ def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def check_grads(grads, gold, tol, report=None):
-    """Compare a grads dict against the golden's bias grads / sub-sampled weight grads."""
+def check_grads(grads, gold, tol, report=None, norm="max"):
+    """Compare a grads dict against the golden's bias grads / sub-sampled weight grads.  norm="max": max|a-b| / max|b|
+    per tensor; norm="l2": ||a-b|| / ||b|| (for the ill-conditioned inverse-depth cases, where single entries of two
+    correct fp32 evaluations differ like phase noise and the max over a tensor is a heavy-tailed statistic)."""
+    def dist(a, b):
+        if norm == "l2":
+            return np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30)
+        return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
     worst = 0.0
     for k, g in grads.items():
         g = g.detach().cpu().double().numpy()
         if k in gold:
             ref = gold[k]
-            e = np.abs(g - ref).max() / max(np.abs(ref).max(), 1e-30)
+            e = dist(g, ref)
         elif k + ".sub" in gold:
             ref = gold[k + ".sub"]
-            e = np.abs(common.subsample(g) - ref).max() / max(np.abs(ref).max(), 1e-30)
+            e = dist(common.subsample(g), ref)
             ss = np.sqrt((g ** 2).sum())
             e = max(e, abs(ss - np.sqrt(gold[k + ".sumsq"])) / max(np.sqrt(gold[k + ".sumsq"]), 1e-30))
         else:
