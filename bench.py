@@ -437,8 +437,9 @@ def graphed_flag(args, launches_per_graph):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel group of one step, from `ncu --set full` captures
-TRAFFIC = {"c2": 4.752e9}
-TRAFFIC_SOURCE = "profiles/r01_ncu_chain.md (ncu --set full, per step)"
+# (taped forward 1.228 GB, dgrad 1.138 GB, wgrad 2.391 GB at the c2 shape)
+TRAFFIC = {"c2": 4.757e9}
+TRAFFIC_SOURCE = "profiles/r02_ncu_chain.md (ncu --set full of tc_mlp_fwd / dgrad / wgrad, per step)"
 
 
 # ------------------------------------------------------------------------------------------------ reference arms

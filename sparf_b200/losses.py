@@ -99,9 +99,7 @@ from .sampling_strategies import sample_rays  # noqa: E402,F401  (sampling_strat
 def _bottom_row(device, dtype=torch.float32) -> torch.Tensor:
     """[0, 0, 0, 1] built ON the device (a python-list constructor is a pageable host->device copy: a synchronisation,
     and illegal inside a CUDA-graph capture)."""
-    row = torch.zeros(4, device=device, dtype=dtype)
-    row[3] = 1
-    return row
+    return torch.cat((torch.zeros(3, device=device, dtype=dtype), torch.ones(1, device=device, dtype=dtype)))
 
 
 def _with_defaults(defaults: Dict[str, Any], opt) -> edict:
@@ -408,7 +406,7 @@ class CorrespondencesPairRenderDepthAndGet3DPtsAndReproject(BaseLoss):
         if iteration < self.opt.precrop_iters:
             dH, dW = int(H // 2 * self.opt.precrop_frac), int(W // 2 * self.opt.precrop_frac)
             center = torch.zeros_like(mask)
-            center[H // 2 - dH:H // 2 + dH - 1, W // 2 - dW:W // 2 + dW - 1] = 1
+            center[H // 2 - dH:H // 2 + dH - 1, W // 2 - dW:W // 2 + dW - 1].fill_(1)   # (fill_: no host scalar copy)
             mask = mask & center
         mask = mask.reshape(-1)
         enough = (mask.sum() >= self.opt.min_nbr_matches).float()        # corres_loss / base_corres_loss early return
