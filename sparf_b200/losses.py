@@ -40,15 +40,19 @@ def from_homogeneous(p: torch.Tensor) -> torch.Tensor:
     return p[..., :-1] / (p[..., -1:] + 1e-6)
 
 
+def _bottom_row(device, dtype=torch.float32) -> torch.Tensor:
+    """[0, 0, 0, 1] built ON the device (a python-list constructor is a pageable host->device copy: a synchronisation,
+    and illegal inside a CUDA-graph capture)."""
+    return torch.cat((torch.zeros(3, device=device, dtype=dtype), torch.ones(1, device=device, dtype=dtype)))
+
+
 def pose_inverse_4x4(mat: torch.Tensor) -> torch.Tensor:
     """[...,4,4] rigid inverse without a matrix inverse: [R^T | -R^T t]."""
-    out = torch.zeros_like(mat)
     R, t = mat[..., :3, :3], mat[..., :3, 3:]
     Rt = R.transpose(-1, -2)
-    out[..., :3, :3] = Rt
-    out[..., :3, 3:] = -Rt @ t
-    out[..., 3, 3] = 1
-    return out
+    top = torch.cat((Rt, -Rt @ t), dim=-1)
+    bottom = _bottom_row(mat.device, mat.dtype).expand(*mat.shape[:-2], 1, 4)    # (no scalar setitem: that is a host copy)
+    return torch.cat((top, bottom), dim=-2)
 
 
 def batch_backproject_to_3d(kpi, di, Ki, T_itoj):
@@ -94,12 +98,6 @@ def get_nearest_pose_ids(tar_pose_c2w: np.ndarray, ref_poses_c2w: np.ndarray, ta
 
 
 from .sampling_strategies import sample_rays  # noqa: E402,F401  (sampling_strategies.py:250-295)
-
-
-def _bottom_row(device, dtype=torch.float32) -> torch.Tensor:
-    """[0, 0, 0, 1] built ON the device (a python-list constructor is a pageable host->device copy: a synchronisation,
-    and illegal inside a CUDA-graph capture)."""
-    return torch.cat((torch.zeros(3, device=device, dtype=dtype), torch.ones(1, device=device, dtype=dtype)))
 
 
 def _with_defaults(defaults: Dict[str, Any], opt) -> edict:
