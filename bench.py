@@ -376,9 +376,16 @@ def run_ours(args):
         torch.cuda.synchronize()
         ar_us = e0.elapsed_time(e1) * 1e3 / 20
     clocks = sampler.stop() if rank == 0 else None   # sampled over the device-timed AND the end-to-end region
+    launched_as_graph = graphed is not None
+    if world > 1:
+        # a CUDA graph that captured NCCL kernels must be gone before the communicator is torn down
+        graphed = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown_distributed(dist)
         return
     peaks = load_peaks()
     ms_per_step = total_ms / args.steps
@@ -404,7 +411,7 @@ def run_ours(args):
                     traffic_source=TRAFFIC_SOURCE, engine=args.engine)
     cpu = tgb = None
     if world == 1 and not args.no_baselines:   # reported on rank 0 at N = 1 only
-        del graphed
+        graphed = None
         torch.cuda.empty_cache()
         try:
             tgb = torch_gpu_baseline(args.config, dev)
@@ -417,7 +424,7 @@ def run_ours(args):
                 config=dict(workload=cfg["desc"], name=args.config, rays_per_gpu=rays_local, global_rays=rays_per_step,
                             samples_per_ray=cfg["S"], fine_samples_per_ray=(cfg["S"] + cfg["S_fine"]) if cfg["fine"] else 0,
                             l2_flush_between_steps=True,
-                            launch="one CUDA-graph replay per step" if graphed_flag(args, launches_per_graph) else "eager",
+                            launch="one CUDA-graph replay per step" if launched_as_graph else "eager",
                             eager_ms_per_step=eager_ms_per_step,
                             timing="mean of per-step CUDA-event intervals, max over ranks",
                             parallelism="dp%d (ray sharding, one NCCL all-reduce of [MLP | pose] grads per step%s)"
@@ -427,13 +434,27 @@ def run_ours(args):
                 e2e=dict(value=rays_per_step / (e2e_ms / args.steps * 1e-3), unit="rays/s",
                          h2d_bytes_per_step=n_view * 8, d2h_bytes_per_step=4),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, torch_gpu_baseline=tgb)
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        shutdown_distributed(dist)
+
+
+def shutdown_distributed(dist, grace_s=15.0):
+    """destroy_process_group() with a watchdog: the measurement is printed already, a communicator that does not tear
+    down cleanly must not keep the launcher (and the GPUs) busy until somebody's timeout fires."""
+    done = threading.Event()
+
+    def watchdog():
+        if not done.wait(grace_s):
+            sys.stderr.write("bench: destroy_process_group() did not return within %.0f s; exiting\n" % grace_s)
+            sys.stderr.flush()
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    try:
         dist.destroy_process_group()
-
-
-def graphed_flag(args, launches_per_graph):
-    return bool(args.graph) and launches_per_graph is not None
+    finally:
+        done.set()
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel group of one step, from `ncu --set full` captures
