@@ -37,12 +37,29 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (+ the flags).  File times are useless here: the tree is
+    copied to the GPU box, where every file gets a fresh mtime and N ranks would all decide to rebuild at once."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in sorted(sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))):
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or os.path.getsize(LIB_PATH) < 4096:
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(HASH_PATH) as f:
+            return f.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 TRACE_LIB_PATH = os.path.join(LIB_DIR, "libsparf_b200_trace.so")   # debug build (tools/trace_chain.py), never loaded by default
@@ -57,13 +74,28 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False, varia
     if not trace and not variant and not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
+    # one builder at a time (several ranks of one job may get here together); whoever waited re-checks first
+    import fcntl
+    lock = open(os.path.join(LIB_DIR, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not trace and not variant and not force and not _stale():
+            return LIB_PATH
+        return _build_locked(out_path, verbose, trace, defines_extra, main_lib=not trace and not variant)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(out_path, verbose, trace, defines_extra, main_lib):
     srcs = sources()
     defines = ["-DSPARF_WITH_TC"] if os.path.exists(os.path.join(CSRC, "mlp_tc.cu")) else []
     defines += os.environ.get("SPARF_NVCC_DEFINES", "").split()   # extra debug defines
     if trace:
         defines.append("-DSPARF_TC_TRACE")
     defines += list(defines_extra)
-    cmd = [_nvcc()] + NVCC_FLAGS + defines + ["-I", INCLUDE, "-o", out_path + ".tmp"] + srcs
+    tmp = "%s.tmp.%d" % (out_path, os.getpid())
+    cmd = [_nvcc()] + NVCC_FLAGS + defines + ["-I", INCLUDE, "-o", tmp] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -73,7 +105,10 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False, varia
         raise RuntimeError("nvcc failed building libsparf_b200.so")
     if verbose:
         print(res.stdout + res.stderr)
-    os.replace(out_path + ".tmp", out_path)
+    os.replace(tmp, out_path)
+    if main_lib:
+        with open(HASH_PATH, "w") as f:
+            f.write(_source_hash())
     return out_path
 
 
