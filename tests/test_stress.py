@@ -16,3 +16,25 @@ def test_cold_l2_repetitions_are_reproducible(monkeypatch, capsys):
     monkeypatch.setattr(sys, "argv", ["stress_chain.py", "40"])
     stress_chain.main()
     assert "stress ok: 40 repetitions" in capsys.readouterr().out
+
+
+# every kernel variant that stays selectable (the knobs are read once per process, hence subprocesses), plus a batch
+# larger than one backward chunk (chunked tape walk with accumulating gradients)
+VARIANTS = [
+    ("shared-memory-operand chain kernels", {"SPARF_TC_TMEMA": "0"}, ["25"]),
+    ("CTA-pair chain kernels", {"SPARF_TC_PAIRS": "1"}, ["25"]),
+    ("no side stream", {"SPARF_TC_OVERLAP": "0"}, ["25"]),
+    ("recompute backward (no tape)", {"STRESS_TAPE": "0"}, ["25"]),
+    ("two backward chunks", {}, ["15", "1100", "128"]),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("what,env,argv", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_cold_l2_stress_of_selectable_variants(what, env, argv):
+    import subprocess
+    e = dict(os.environ)
+    e.update(env)
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_chain.py")] + argv, env=e, capture_output=True,
+                         text=True, timeout=300)
+    assert res.returncode == 0 and "stress ok: %s repetitions" % argv[0] in res.stdout, (what, res.stdout[-500:], res.stderr[-1500:])

@@ -15,7 +15,8 @@ from sparf_b200 import _lib, ops
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
-    R, S = 1023, 128
+    R, S = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1023, 128)
+    ops.USE_TAPE[0] = os.environ.get("STRESS_TAPE", "1") != "0"    # 0: the recompute (no tape) backward
     opt = common.make_opt(S=S)
     sd = common.det_weights(opt, 0)
     keys = sum([["mlp_feat.%d.weight" % i, "mlp_feat.%d.bias" % i] for i in range(8)], []) + \
