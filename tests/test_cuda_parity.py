@@ -167,22 +167,19 @@ def test_graph_end_to_end_vs_reference(name, engine):
     print(name, engine, {k: "%.1e" % v for k, v in report.items()}, "worst grad %.1e" % worst)
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-def test_c4_inverse_depth_error_vs_fp64(engine):
-    """Inverse-depth case (BASELINE config 4): our error is gated against the REFERENCE's OWN fp32 error on the same
-    inputs, both measured from the exact (fp64) evaluation (tests/test_oracle_vs_golden.py::
-    test_inverse_depth_conditioning_c4 explains the conditioning): outputs and gradients must be no further from the
-    truth than 1.5x the reference is (floor: north_star's 1e-4); gradient tensors: 6x in relative L2 (floor 1e-3; measured 0.5x .. 4.4x)."""
+def _error_vs_fp64(name, engine, out_factor, grad_factor, grad_floor):
+    """Our distance from the exact (fp64-oracle) result of a golden case, gated against the REFERENCE's own fp32 distance
+    from it (the golden holds the reference's outputs and gradients): outputs max-norm, gradient tensors relative L2."""
     from helpers import replay_oracle
-    exact_out, _, exact_grads, gold = replay_oracle("c4_inverse_pixels", torch.float64)
-    out, loss, grads, _ = replay_graph("c4_inverse_pixels", engine)
+    exact_out, _, exact_grads, gold = replay_oracle(name, torch.float64)
+    out, loss, grads, _ = replay_graph(name, engine)
     rep = {}
     for k in ("rgb", "depth", "opacity"):
         ex = exact_out[k].detach().numpy()
         ours = rel_err(out[k].detach().cpu().numpy().reshape(ex.shape), ex)
         ref = rel_err(gold["out_" + k].reshape(ex.shape), ex)
         rep[k] = (ours, ref)
-        assert ours <= max(1.5 * ref, 1e-4), (k, ours, ref)
+        assert ours <= max(out_factor * ref, 1e-4), (name, k, ours, ref)
     for k, g in grads.items():
         ex = exact_grads[k].detach().numpy()
         mine = g.detach().cpu().double().numpy()
@@ -190,14 +187,35 @@ def test_c4_inverse_depth_error_vs_fp64(engine):
             ref_g = gold[k]
         else:
             ref_g, ex, mine = gold[k + ".sub"], common.subsample(ex), common.subsample(mine)
-        # gradients: relative L2 distance per tensor (single entries behave like phase noise: our rays differ from the
-        # reference's in the last bit, and at t ~ 256 that alone moves an entry by ~1e-2 -- the max over a tensor of two
-        # independent such evaluations is heavy-tailed, measured ratios 0.5 .. 7)
         scale = max(np.sqrt((ex ** 2).sum()), 1e-30)
         ours, ref = np.sqrt(((mine - ex) ** 2).sum()) / scale, np.sqrt(((ref_g - ex) ** 2).sum()) / scale
         rep[k] = (ours, ref)
-        assert ours <= max(6 * ref, 1e-3), (k, ours, ref)
-    print(engine, "worst ours/ref error ratio %.2f" % max(a / max(b, 1e-12) for a, b in rep.values()))
+        assert ours <= max(grad_factor * ref, grad_floor), (name, k, ours, ref)
+    worst = max(rep.items(), key=lambda kv: kv[1][0] / max(kv[1][1], 1e-12))
+    print(name, engine, "worst ours / reference-fp32 distance from fp64: %s %.1e / %.1e" % (worst[0], worst[1][0], worst[1][1]))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_c4_inverse_depth_error_vs_fp64(engine):
+    """Inverse-depth case (BASELINE config 4): our error is gated against the REFERENCE's OWN fp32 error on the same
+    inputs, both measured from the exact (fp64) evaluation (tests/test_oracle_vs_golden.py::
+    test_inverse_depth_conditioning_c4 explains the conditioning): outputs no further from the truth than 1.5x the
+    reference is (floor: north_star's 1e-4); gradient tensors: 6x in relative L2 (floor 1e-3; measured 0.5x .. 4.4x --
+    single entries behave like phase noise: our rays differ from the reference's in the last bit, and at t ~ 256 that
+    alone moves an entry by ~1e-2)."""
+    _error_vs_fp64("c4_inverse_pixels", engine, 1.5, 6.0, 1e-3)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["c1_coarse", "c3_barf_pose"])
+def test_coarse_cases_error_vs_fp64(name, engine):
+    """The same yardstick for the metric-depth goldens without a resampling step (c1; c3 with pose gradients, BARF mask
+    and sigma noise): outputs within 2x and gradient tensors within 3x (relative L2) of the reference's own fp32 distance
+    from the exact result, floors 1e-4 / 1e-3 -- the tight gate of the tcgen05 engine's gradients, which the comparison
+    with the golden alone (6e-2, the reference's own noise) cannot give.  (Hierarchical cases are excluded: a last-bit
+    change of a coarse weight moves a resampled position discontinuously, in exact arithmetic as well; the headline-shape
+    test tests/test_headline_parity.py covers the full-size batch the same way.)"""
+    _error_vs_fp64(name, engine, 2.0, 3.0, 1e-3)
 
 
 @pytest.mark.parametrize("engine", ENGINES)
