@@ -2024,6 +2024,9 @@ bool tc_supports(const SparfMLP* mlp) {
 
 bool tc_backward_available() { return true; }
 static int tape_tiles(int R, int S);
+static size_t tape_off_denc(int R, int S);
+static size_t tape_off_packed_b(int R, int S);
+static size_t tape_off_packed_e(int R, int S);
 
 // rays per backward chunk: <= 1024 row tiles of gradient images (~1.1 GB), a whole number of 128-row tiles (a taped
 // forward numbers its tiles over the whole batch, so every chunk has to start on a tile boundary)
@@ -2274,6 +2277,38 @@ int tc_mlp_forward(const SparfMLP* mlp, int engine, int R, int S, const float* o
                         raybias, nullptr, st, weight_copies());
 }
 
+// Fork / join onto a library-owned side stream (one per device, created on first use): the CUDA-core leftovers of the
+// backward (bias / narrow-layer reductions, view-direction columns, ray gradients) only depend on the dgrad chain, so
+// they run BESIDE the HBM-bound weight-gradient kernel instead of after it (its CTAs leave ~30 KB of shared memory and
+// most thread slots of every SM free).  Event record / wait pairs make the pattern capturable into a CUDA graph.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t raybias = nullptr, packed = nullptr;   // taped forward: raybias ready / backward weight streams packed
+};
+static SideStream* side_stream() {
+  static SideStream table[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideStream& s = table[dev & 63];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.raybias, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.packed, cudaEventDisableTiming);
+  }
+  return &s;
+}
+static bool overlap_small_kernels() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPARF_TC_OVERLAP");     // 0: everything on the caller's stream (debugging / A-B timing)
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // Training forward: same fp16-split arithmetic and outputs as tc_mlp_forward, plus the tape for the backward.
 int tc_mlp_forward_tape(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
                         const float* t, const float* noise, float* sigma, float* rgb, void* tape, size_t tape_bytes,
@@ -2293,27 +2328,57 @@ int tc_mlp_forward_tape(const SparfMLP* mlp, int engine, int R, int S, const flo
   float* raybias = reinterpret_cast<float*>(packed + align_up((size_t)kChunksPerTile * kChunkBytes, 256));
   const int ntiles = tape_tiles(R, S);
   uint8_t* tp = reinterpret_cast<uint8_t*>(tape);
-  float* denc = reinterpret_cast<float*>(tp + align_up(fwd_images_bytes(ntiles), 1024));
+  float* denc = reinterpret_cast<float*>(tp + tape_off_denc(R, S));
+  C2F c2f{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
+  // side stream: the per-ray colour-head bias (needed by the forward kernel) and the two weight streams of the
+  // BACKWARD (needed only by sparf_mlp_backward_tape) run beside the forward packing / kernel
+  SideStream* side = overlap_small_kernels() ? side_stream() : nullptr;
+  cudaStream_t sd = st;
+  if (side) {
+    SPARF_CHECK_CUDA(cudaEventRecord(side->fork, st));
+    SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    sd = side->stream;
+  }
+  raybias_kernel<<<ceil_div(R, 4), 512, 0, sd>>>(R, dirs, mlp->head_w[0], mlp->head_b[0], c2f, raybias, denc);
+  SPARF_CHECK_LAUNCH("raybias_kernel");
+  if (side) SPARF_CHECK_CUDA(cudaEventRecord(side->raybias, side->stream));
   PackParams pp;
   fill_pack_params(mlp, pp, packed);
   pp.order = fwd_variant(true, 3, true, ntiles) == FWD_TMEM ? 1 : 0;
   pack_weights_kernel<true><<<kChunksPerTile, 256, 0, st>>>(pp);
   SPARF_CHECK_LAUNCH("pack_weights_kernel");
-  C2F c2f{mlp->use_c2f, mlp->c2f_start, mlp->c2f_range, mlp->progress};
-  raybias_kernel<<<ceil_div(R, 4), 512, 0, st>>>(R, dirs, mlp->head_w[0], mlp->head_b[0], c2f, raybias, denc);
-  SPARF_CHECK_LAUNCH("raybias_kernel");
+  PackParams pb;
+  fill_pack_params(mlp, pb, tp + tape_off_packed_b(R, S));
+  pack_weights_bwd_kernel<<<kBwdChunksPerTile, 256, 0, sd>>>(pb);
+  SPARF_CHECK_LAUNCH("pack_weights_bwd_kernel");
+  pack_weights_enc_kernel<<<16, 256, 0, sd>>>(mlp->trunk_w[4], mlp->trunk_w[0], tp + tape_off_packed_e(R, S));
+  SPARF_CHECK_LAUNCH("pack_weights_enc_kernel");
+  if (side) {
+    SPARF_CHECK_CUDA(cudaEventRecord(side->packed, side->stream));
+    SPARF_CHECK_CUDA(cudaStreamWaitEvent(st, side->raybias, 0));
+  }
   Images img;
   images_assign(img, ntiles, tp, nullptr);
-  return launch_forward(mlp, true, 3, R, S, origins, dirs, t, noise, sigma, rgb, packed, raybias, &img, st);
+  rc = launch_forward(mlp, true, 3, R, S, origins, dirs, t, noise, sigma, rgb, packed, raybias, &img, st);
+  // join: whatever follows on the caller's stream (the backward, or a reuse of the tape's memory) is ordered after the
+  // side-stream packing, which has long finished by the time the forward kernel ends
+  if (side && rc == SPARF_OK) SPARF_CHECK_CUDA(cudaStreamWaitEvent(st, side->packed, 0));
+  return rc;
 }
 
 // tape = what the training forward keeps for the backward: the forward operand images of every row tile
 // followed by the per-ray view-direction encoding [R,32]
 static int tape_tiles(int R, int S) { return (int)(((long long)R * S + kTileM - 1) / kTileM); }
 constexpr size_t kMaxTapeBytes = (size_t)64 << 30;   // beyond this the backward recomputes the forward chunk by chunk
+// tape = forward operand images | per-ray view-direction encoding [R,32] | backward weight stream (120 x 16 KB) |
+//        ray-gradient weight stream (128 KB): the two packed streams are produced by the FORWARD call on the side
+//        stream, beside the forward kernel, so the backward starts with its dgrad chain
+static size_t tape_off_denc(int R, int S) { return align_up(fwd_images_bytes(tape_tiles(R, S)), 1024); }
+static size_t tape_off_packed_b(int R, int S) { return tape_off_denc(R, S) + align_up((size_t)R * 32 * 4, 1024); }
+static size_t tape_off_packed_e(int R, int S) { return tape_off_packed_b(R, S) + (size_t)kBwdChunksPerTile * kChunkBytes; }
 size_t tc_tape_bytes(const SparfMLP* mlp, int R, int S) {
   if (!tc_supports(mlp)) return 0;
-  const size_t need = align_up(fwd_images_bytes(tape_tiles(R, S)), 1024) + align_up((size_t)R * 32 * 4, 1024);
+  const size_t need = tape_off_packed_e(R, S) + kEgWBytes;
   return need <= kMaxTapeBytes ? need : 0;
 }
 
@@ -2341,35 +2406,6 @@ int tc_mlp_backward_tape(const SparfMLP* mlp, int engine, int R, int S, const fl
   }
   return tc_mlp_backward_impl(mlp, engine, R, S, origins, dirs, t, nullptr, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace,
                               workspace_bytes, reinterpret_cast<uint8_t*>(tape), sigma, rgb, st);
-}
-
-// Fork / join onto a library-owned side stream (one per device, created on first use): the CUDA-core leftovers of the
-// backward (bias / narrow-layer reductions, view-direction columns, ray gradients) only depend on the dgrad chain, so
-// they run BESIDE the HBM-bound weight-gradient kernel instead of after it (its CTAs leave ~30 KB of shared memory and
-// most thread slots of every SM free).  Event record / wait pairs make the pattern capturable into a CUDA graph.
-struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
-static SideStream* side_stream() {
-  static SideStream table[64];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  SideStream& s = table[dev & 63];
-  if (!s.stream) {
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
-  }
-  return &s;
-}
-static bool overlap_small_kernels() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SPARF_TC_OVERLAP");     // 0: everything on the caller's stream (debugging / A-B timing)
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
 }
 
 static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, const float* origins, const float* dirs,
@@ -2400,7 +2436,9 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
                   // [m0 / 128, ...) of it (bwd_chunk_rays keeps every chunk on a tile boundary)
       const int ntiles_all = tape_tiles(R, S);
       images_assign(img, ntiles_all, tape, c.images_b, (int)(m0 / kTileM), ntiles);
-      c.denc = reinterpret_cast<float*>(tape + align_up(fwd_images_bytes(ntiles_all), 1024)) + (size_t)r0 * 32;
+      c.denc = reinterpret_cast<float*>(tape + tape_off_denc(R, S)) + (size_t)r0 * 32;
+      c.packed_b = tape + tape_off_packed_b(R, S);      // packed by the forward call (side stream)
+      c.packed_e = tape + tape_off_packed_e(R, S);
       c.sigma = const_cast<float*>(sigma_fwd) + m0;
       c.rgb = const_cast<float*>(rgb_fwd) + m0 * 3;
     } else {
@@ -2413,9 +2451,11 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       pack_weights_kernel<false><<<kChunksPerTile, 256, 0, st>>>(pp);
       SPARF_CHECK_LAUNCH("pack_weights_kernel<bf16>");
     }
-    fill_pack_params(mlp, pp, c.packed_b);
-    pack_weights_bwd_kernel<<<kBwdChunksPerTile, 256, 0, st>>>(pp);
-    SPARF_CHECK_LAUNCH("pack_weights_bwd_kernel");
+    if (!tape) {
+      fill_pack_params(mlp, pp, c.packed_b);
+      pack_weights_bwd_kernel<<<kBwdChunksPerTile, 256, 0, st>>>(pp);
+      SPARF_CHECK_LAUNCH("pack_weights_bwd_kernel");
+    }   // (with a tape the forward call packed both backward weight streams on the side stream and joined)
     if (!tape) {
       raybias_kernel<<<ceil_div(nr, 4), 512, 0, st>>>(nr, dirs + (size_t)r0 * 3, mlp->head_w[0], mlp->head_b[0], c2f, c.raybias, c.denc);
       SPARF_CHECK_LAUNCH("raybias_kernel");
@@ -2511,8 +2551,10 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
 
     // 5. gradients w.r.t. the rays (camera-pose optimisation)
     if (d_origins != nullptr || d_dirs != nullptr) {
-      pack_weights_enc_kernel<<<16, 256, 0, sd>>>(mlp->trunk_w[4], mlp->trunk_w[0], c.packed_e);
-      SPARF_CHECK_LAUNCH("pack_weights_enc_kernel");
+      if (!tape) {
+        pack_weights_enc_kernel<<<16, 256, 0, sd>>>(mlp->trunk_w[4], mlp->trunk_w[0], c.packed_e);
+        SPARF_CHECK_LAUNCH("pack_weights_enc_kernel");
+      }
       EncGradParams ep;
       ep.packed = c.packed_e; ep.img = img; ep.t = t + m0;
       ep.d_origins = d_origins ? d_origins + (size_t)r0 * 3 : nullptr;

@@ -178,11 +178,14 @@ class Loss:
         return loss_dict
 
     def summarize_loss_w_predefined_weights(self, opt, loss_dict):
-        total, extra = 0.0, {}
+        total, extra = None, {}
         for key in self._checked(opt, loss_dict):
             w = 10 ** float(opt.loss_weight[key]) if opt.loss_weight.parametrization == "exp" else float(opt.loss_weight[key])
-            extra[key + "_after_w"] = w * loss_dict[key]
-            total = total + extra[key + "_after_w"]
+            # (w == 1, the photometric term: the same value without a multiply kernel; first term: no `0.0 + x` kernel)
+            extra[key + "_after_w"] = loss_dict[key] if w == 1.0 else w * loss_dict[key]
+            total = extra[key + "_after_w"] if total is None else total + extra[key + "_after_w"]
+        if total is None:
+            total = 0.0
         loss_dict.update(all=total)
         loss_dict.update(extra)
         return loss_dict

@@ -297,6 +297,9 @@ class CompositeFunction(torch.autograd.Function):
         ctx.white_bg = bool(white_bg)
         ctx.save_for_backward(sigma, rgb, t, dirs)
         ctx.mark_non_differentiable(depth_var, rgb_var, all_cum)
+        # outputs nobody differentiated arrive as None in backward (the C ABI takes NULL) instead of as freshly
+        # zero-filled tensors: six fill kernels and a [R,S] write + read less per render call
+        ctx.set_materialize_grads(False)
         return rgb_map, depth, opacity, weights, depth_var, rgb_var, all_cum
 
     @staticmethod
@@ -345,6 +348,7 @@ class RayGenFunction(torch.autograd.Function):
         check(L.sparf_raygen_forward(B, n, int(W), _ptr(pose_w2c), _ptr(intr_inv), _ptr(idx), _ptr(pixels), per_image,
                                      _ptr(origins), _ptr(dirs), _stream()), "raygen_forward")
         ctx.args = (B, n, int(W), per_image)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(pose_w2c, intr_inv, idx if idx is not None else torch.empty(0), pixels if pixels is not None else torch.empty(0))
         ctx.has_idx = idx is not None
         return origins, dirs
@@ -355,6 +359,8 @@ class RayGenFunction(torch.autograd.Function):
         L = _lib.lib()
         pose_w2c, intr_inv, idx, pixels = ctx.saved_tensors
         B, n, W, per_image = ctx.args
+        if g_o is None and g_d is None:
+            return None, None, None, None, None
         d_pose = torch.zeros_like(pose_w2c)
         g_o = _f32c(g_o) if g_o is not None else None
         g_d = _f32c(g_d) if g_d is not None else None

@@ -187,8 +187,15 @@ class Graph(torch.nn.Module):
                               depth_range=depth_range, iter=iter)
             ret.ray_idx = ray_idx
         ret.idx_img_rendered = torch.from_numpy(np.array(img_idx)).to(self.device) if img_idx is not None else \
-            torch.arange(start=0, end=batch_size, device=self.device)
+            self._arange(batch_size)
         return ret
+
+    def _arange(self, n):
+        """arange(n) on the device, built once per n (the reference rebuilds it on every call, renderer.py:246)."""
+        cache = self.__dict__.setdefault("_arange_cache", {})
+        if n not in cache:
+            cache[n] = torch.arange(start=0, end=n, device=self.device)
+        return cache[n]
 
     # ---------------------------------------------------------------------------- core
     def render(self, opt, pose, H, W, intr, pixels=None, ray_idx=None, depth_range=None, iter=None, mode=None):
