@@ -74,3 +74,32 @@ def test_two_rank_allreduce_matches_single_process():
     assert len(mine0) == 52
     assert abs(total1.item() - total2) < 1e-5 * max(1.0, total2)
     assert torch.allclose(fg.flat, flat2, rtol=1e-4, atol=1e-7)
+
+
+def test_flat_gradients_detect_detached_grads():
+    """optimizer.zero_grad() (set_to_none=True) detaches every .grad from the flat buffer: the next collective must
+    re-attach (None) or refuse (foreign storage) instead of silently reducing stale zeros; `progress` is left out."""
+    import pytest
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(4, 3)
+            self.progress = torch.nn.Parameter(torch.tensor(0.0))
+
+    net = Net()
+    fg = FlatGradients([net])
+    assert fg.flat.numel() == 4 * 3 + 3 and all(p is not net.progress for p in fg.params)
+    assert all(getattr(p, "_sparf_inplace_grad", False) for p in fg.params) and not hasattr(net.progress, "_sparf_inplace_grad")
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    net.lin(torch.ones(2, 4)).sum().backward()
+    assert fg.flat.abs().sum() > 0
+    opt.zero_grad()                                   # set_to_none=True: .grad = None
+    assert net.lin.weight.grad is None
+    fg.zero_()                                        # re-attaches
+    assert net.lin.weight.grad.data_ptr() == fg.flat.data_ptr()
+    net.lin(torch.ones(2, 4)).sum().backward()
+    assert fg.flat.abs().sum() > 0
+    net.lin.weight.grad = torch.zeros_like(net.lin.weight)     # foreign storage
+    with pytest.raises(RuntimeError, match="no longer aliases"):
+        fg.all_reduce()
