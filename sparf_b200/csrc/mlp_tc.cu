@@ -688,6 +688,33 @@ constexpr int kFwdSlots = SPARF_FWD_SLOTS, kDgSlots = SPARF_DG_SLOTS, kStoreInfl
 static_assert(kFwdSlots <= kMaxSlots && kDgSlots <= kMaxSlots && kStoreInflight >= 1 && kStoreInflight < kFwdSlots &&
               kStoreInflight < kDgSlots, "staging slots / stores in flight");
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// SPARF_STORE_LSU = 1 (experiment, default off): the store warp(s) copy a staged block to HBM with ordinary 16-byte
+// loads / stores (ld.shared -> st.global, 512 contiguous bytes per warp instruction) instead of a bulk copy, and the
+// epilogue warps drop their generic -> async proxy fence.  Measured SLOWER (profiles/r02_notes.md): a warp needs
+// ~1190 clk per 16 KB block this way (the bulk copy: ~1040) because it shares issue slots and the LSU with the epilogue
+// warps; taped forward 427 -> 436 us, dgrad 306 -> 337 us.
+#ifndef SPARF_STORE_LSU
+#define SPARF_STORE_LSU 0
+#endif
+constexpr bool kStoreLsu = SPARF_STORE_LSU != 0;
+// LSU mode: number of store warps (1: warp 19; 2: + warp 18, the second-issuer warp the TMEM-operand kernels leave idle);
+// store warp i takes the staged blocks with running index % kStoreWarps == i
+#ifndef SPARF_STORE_WARPS
+#define SPARF_STORE_WARPS 2
+#endif
+constexpr int kStoreWarps = kStoreLsu ? SPARF_STORE_WARPS : 1;
+// whole warp: copy `bytes` (multiple of 4096) from shared to global memory, streaming stores
+__device__ __forceinline__ void warp_copy_s2g(uint8_t* gdst, const uint8_t* ssrc, int bytes, int lane) {
+  const uint4* src = reinterpret_cast<const uint4*>(ssrc) + lane;
+  uint4* dst = reinterpret_cast<uint4*>(gdst) + lane;
+  for (int i = 0; i < bytes / 512; i += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = src[(i + u) * 32];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) __stcs(dst + (i + u) * 32, v[u]);
+  }
+}
 constexpr int kOffEncT = 0;
 constexpr int kOffStgT = 2 * kChunkBytes;
 constexpr int kOffRingTSave = kOffStgT + kFwdSlots * kChunkBytes, kStagesTSave = SPARF_FWD_RING;
@@ -746,7 +773,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   if (warp == 0) {
     if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
     else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1);
-  } else if (warp == 1 || warp == 2 + kEpiWarps) {
+  } else if (warp == 1 || (warp == 2 + kEpiWarps && !(kTmemA && kStoreWarps == 2))) {
     const int issuer = warp == 1 ? 0 : 1;
     // ============================== MMA issuer ==============================
     if (kPair && issuer != 0) {
@@ -855,9 +882,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
       }
       if (lane == 0 && issuer == 0) trace_end(tr, 1);
     }
-  } else if (kTmemA && warp == 2 + kEpiWarps + kIssuers - 1) {
-    // ============================== tape store warp ==============================
-    // streams the bf16 tape images of layers 0..7 out of the three rotating staging slots (one 16 KB block each)
+  } else if (kTmemA && warp >= 2 + kEpiWarps) {
+    // ============================== tape store warp(s) ==============================
+    // stream the bf16 tape images of layers 0..7 out of the rotating staging slots (one 16 KB block each)
+    const uint32_t store_id = (uint32_t)(2 + kEpiWarps + kIssuers - 1 - warp);   // warp 19 -> 0, warp 18 -> 1
     if (p.save) {
       uint8_t* stg = smem + kOffStgT;
       Trace tr; trace_begin(tr);
@@ -867,10 +895,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
           const int t_img = l == 7 ? T_FEAT : T_H0 + l;
           for (int jp = 0; jp < 8; ++jp) {                         // (block j, part)
             const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + (uint32_t)jp;
+            if (qs % (uint32_t)kStoreWarps != store_id) continue;
             const uint32_t slot = qs % (uint32_t)kFwdSlots, k = qs / (uint32_t)kFwdSlots;
             twait(tr, 0, &cs.g_ready[slot], k & 1);
             long long t0 = trace_tic();
-            if (elect_one()) {
+            if (kStoreLsu) {
+              warp_copy_s2g(p.img.at(t_img, tile, jp >> 1, jp & 1), stg + (size_t)slot * kChunkBytes, kChunkBytes, lane);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&cs.s_free[slot]);
+            } else if (elect_one()) {
               bulk_s2g(p.img.at(t_img, tile, jp >> 1, jp & 1), stg + (size_t)slot * kChunkBytes, kChunkBytes);
               bulk_commit_group();
               bulk_wait_read<kStoreInflight - 1>();      // every store but the newest kStoreInflight - 1 has read its slot
@@ -882,9 +915,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
           }
         }
       }
-      if (elect_one()) bulk_wait_all();
+      if (!kStoreLsu && elect_one()) bulk_wait_all();
       __syncwarp();
-      if (lane == 0) trace_end(tr, 4);
+      if (lane == 0 && store_id == 0) trace_end(tr, 4);
     }
   } else if (warp < 2 + kEpiWarps) {
     // ============================== epilogue warps ==============================
@@ -1016,7 +1049,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
                   const uint32_t slot = qs % (uint32_t)kFwdSlots, k = qs / (uint32_t)kFwdSlots;
                   if (k > 0) twait(tr, 1, &cs.s_free[slot], (k - 1) & 1);
                   store16_part(part == 0 ? sp.hi : sp.lo, row, cq * kEpiCols, stg + (size_t)slot * kChunkBytes);
-                  fence_proxy_async_smem();
+                  if (!kStoreLsu) fence_proxy_async_smem();   // (LSU store warp: generic proxy on both sides)
                   __syncwarp();
                   if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
                 }
@@ -1200,7 +1233,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
   if (warp == 0) {
     if (kPair) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false);
     else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false);
-  } else if (warp == 1 || warp == 2 + kEpiWarps) {
+  } else if (warp == 1 || (warp == 2 + kEpiWarps && !(kTmemA && kStoreWarps == 2))) {
     const int issuer = warp == 1 ? 0 : 1;
     if (kPair && issuer != 0) {
       // the second issuer warp has no role in a CTA pair
@@ -1262,9 +1295,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
       }
       if (lane == 0) trace_end(tr, 1);
     }
-  } else if (warp == 2 + kEpiWarps + kIssuers - 1) {
-    // ============================== gradient-image store warp ==============================
-    // streams every finished [128 x 64] hi / lo block pair (already in the HBM image layout) out with bulk copies
+  } else if (warp >= 2 + kEpiWarps) {
+    // ============================== gradient-image store warp(s) ==============================
+    // stream every finished [128 x 64] hi / lo block pair (already in the HBM image layout) out
+    const uint32_t store_id = (uint32_t)(2 + kEpiWarps + kIssuers - 1 - warp);   // warp 19 -> 0, warp 18 (TMEM kernel) -> 1
     uint8_t* act_hi = smem + kOffAct;
     uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
     for (int it = 0; it < my_tiles; ++it) {
@@ -1278,11 +1312,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           // index of the (tile, step, block) writes, slot = q & 1, k = q >> 1 its per-slot sequence number
           const uint32_t q = 34u * (uint32_t)it + (step == 0 ? (uint32_t)j : 2u + 4u * (uint32_t)(step - 1) + (uint32_t)j);
           const uint32_t n = j < 2 ? 9u * (uint32_t)it + (uint32_t)step : 8u * (uint32_t)it + (uint32_t)step - 1u;
+          if (kTmemA && q % (uint32_t)kStoreWarps != store_id) continue;
           const int bi = kTmemA ? (int)(q % (uint32_t)kDgSlots) : j;
           const uint8_t* src_hi = kTmemA ? smem + kOffAct + (size_t)bi * 2 * kChunkBytes : act_hi + (size_t)j * kChunkBytes;
           const uint8_t* src_lo = kTmemA ? src_hi + kChunkBytes : act_lo + (size_t)j * kChunkBytes;
           mbar_wait(&cs.g_ready[bi], (kTmemA ? (q / (uint32_t)kDgSlots) : n) & 1);
-          if (elect_one()) {
+          if (kTmemA && kStoreLsu) {
+            if (tile_ok) warp_copy_s2g(p.img.at(t_out, tile, j, 0), src_hi, 2 * kChunkBytes, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cs.s_free[bi]);
+          } else if (elect_one()) {
             if (kTmemA) {
               // (hi | lo) of a block are adjacent in the slot AND in the HBM image: one 32 KB bulk store.  A dummy tile
               // (never with stand-alone CTAs) would still need its (empty) group for the in-flight accounting.
@@ -1305,7 +1344,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         }
       }
     }
-    if (elect_one()) bulk_wait_all();
+    if (!(kTmemA && kStoreLsu) && elect_one()) bulk_wait_all();
     __syncwarp();
   } else {
     const int e = warp - 2;
@@ -1369,7 +1408,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           uint8_t* st_hi = smem + kOffAct + (size_t)slot * 2 * kChunkBytes;
           if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
           store16(sp, row, cq * kEpiCols, st_hi, st_hi + kChunkBytes);
-          fence_proxy_async_smem();
+          if (!kStoreLsu) fence_proxy_async_smem();   // (LSU store warp: generic proxy on both sides)
           __syncwarp();
           if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
         } else {
@@ -1447,7 +1486,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             if (k > 0) mbar_wait(&cs.s_free[slot], (k - 1) & 1);
             trace_toc(tr, 3, tt3);
             store16(sp, row, cq * kEpiCols, st_hi, st_hi + kChunkBytes);
-            fence_proxy_async_smem();
+            if (!kStoreLsu) fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&cs.g_ready[slot]);
           } else {
