@@ -1542,6 +1542,8 @@ struct WgradJob {
   float* colsum;         // optional: colsum[f] += sum_rows G[row][f]  (the layer's bias gradient), else NULL
 };
 constexpr int kMaxWgradJobs = 160;
+constexpr int kBwdSplitDefault = 1;     // sub-chunks of the backward pipeline (dgrad(k + 1) beside wgrad(k)); 1 = off
+constexpr int kBwdNdDefault = 88;       // SMs of the dgrad chain while a weight-gradient kernel runs beside it
 struct WgradJobs { WgradJob j[kMaxWgradJobs]; };   // passed by value (kernel parameter): no host->device copy per step
 constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 16 * 4096;   // (4 G blocks + 4 X blocks) x (hi, lo) x 32 rows x 128 B
@@ -2324,6 +2326,7 @@ struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
   cudaEvent_t raybias = nullptr, packed = nullptr;   // taped forward: raybias ready / backward weight streams packed
+  cudaEvent_t sub[8] = {};                           // backward: dgrad of sub-chunk k finished
 };
 static SideStream* side_stream() {
   static SideStream table[64];
@@ -2336,9 +2339,23 @@ static SideStream* side_stream() {
     cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.raybias, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.packed, cudaEventDisableTiming);
+    for (auto& e : s.sub) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   }
   return &s;
 }
+// Backward pipelining (SPARF_TC_BWD_SPLIT = n sub-chunks, SPARF_TC_BWD_ND = SMs given to the dgrad chain while a
+// weight-gradient kernel runs beside it; 0 / 1 = off): the dgrad chain is tensor-bound, the weight-gradient pass
+// HBM-bound, so dgrad(k + 1) and wgrad(k) run concurrently on disjoint SM sets (grid sizes; one CTA per SM either way).
+static int bwd_split_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+__host__ __device__ inline void images_advance(Images& img, int tile0) {
+  for (int t = 0; t < T_COUNT; ++t)
+    if (img.ptr[t]) img.ptr[t] += (size_t)tile0 * tensor_nblk(t) * 2 * kChunkBytes;
+  if (img.mask) img.mask += (size_t)tile0 * kMaskTileBytes;
+}
+
 static bool overlap_small_kernels() {
   static int v = -1;
   if (v < 0) {
@@ -2512,56 +2529,94 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     bp.g_raw = c.g_raw; bp.g_pre = c.g_pre;
     bp.w7 = mlp->trunk_w[7]; bp.w9 = mlp->head_w[1];
     bp.M = Mc; bp.num_tiles = ntiles; bp.img = img;
-    if (use_cta_pairs(false) && ntiles >= 2) {
+    static const bool tmem_a = !(getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '0');
+    const bool pairs = use_cta_pairs(false) && ntiles >= 2;
+    SideStream* side = overlap_small_kernels() ? side_stream() : nullptr;
+    // sub-chunk pipeline only with the stand-alone TMEM-operand chain kernel and when every sub-chunk still fills the GPU
+    int nsplit = (side && tmem_a && !pairs) ? std::min(8, std::max(1, bwd_split_env("SPARF_TC_BWD_SPLIT", kBwdSplitDefault))) : 1;
+    while (nsplit > 1 && ntiles / nsplit < num_sms()) --nsplit;
+    const int nd_sms = std::max(16, std::min(num_sms() - 16, bwd_split_env("SPARF_TC_BWD_ND", kBwdNdDefault)));
+
+    // 3. (helper) weight-gradient job table = (layer, slab of row tiles) over tiles [t_lo, t_hi), ~`ctas` CTAs, one per SM
+    auto wgrad_launch = [&](int t_lo, int t_hi, int ctas, cudaStream_t ws) -> int {
+      WgradJobs jobs_tab;
+      WgradJob* jobs = jobs_tab.j;
+      int nj = 0;
+      const int nt = t_hi - t_lo;
+      auto add_jobs = [&](int tg, int tx, int mblk, int nblk, float* dW, int ldw, int col0, int enc, int slabs, float* colsum) {
+        slabs = std::max(1, std::min(slabs, nt));
+        for (int sl = 0; sl < slabs; ++sl) {
+          WgradJob j;
+          j.t_g = tg; j.t_x = tx; j.mblk = mblk; j.nblk = nblk;
+          j.tile_begin = t_lo + (int)((long long)nt * sl / slabs);
+          j.tile_end = t_lo + (int)((long long)nt * (sl + 1) / slabs);
+          j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum;
+          jobs[nj++] = j;
+        }
+      };
+      // One CTA per SM in a single wave.  A stage (32 rows of one tile) costs about the same ~2.4k clocks whatever its
+      // width (it is bound by the latency of the 3-deep HBM pipeline, profiles/r01_ncu_chain.md), so the slabs equalise
+      // the number of stages per CTA rather than bytes: 10 job types x ~14.8 slabs = 147 CTAs on a whole GPU.
+      int slabs[10];      // 8 wide job types, then the two encoder-block types
+      const int s_lo = std::max(1, ctas / 10), extra = std::max(0, std::min(8, ctas - 10 * s_lo));
+      for (int i = 0; i < 10; ++i) slabs[i] = s_lo + (i < extra ? 1 : 0);
+      add_jobs(T_GHID, T_FEAT, 2, 4, grad->head_w[0], kW + kEv, 0, 0, slabs[7], grad->head_b[0]);     // head 0, feature part
+      add_jobs(T_G7F, T_H0 + 6, 4, 4, grad->trunk_w[7] + kW, kW, 0, 0, slabs[0], grad->trunk_b[7] + 1);  // trunk 7 rows 1..256
+      for (int l = 6; l >= 1; --l)
+        add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, slabs[7 - l], grad->trunk_b[l]);
+      add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, slabs[8], nullptr);             // skip part of layer 4
+      add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, slabs[9], grad->trunk_b[0]);          // layer 0 (+ its bias)
+      tc_mlp_wgrad_kernel<<<nj, 192, kWgSmem + 1024, ws>>>(jobs_tab, img);
+      SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
+      return SPARF_OK;
+    };
+
+    cudaStream_t sd = st;      // stream of the CUDA-core leftovers (step 4)
+    if (pairs) {
       const int grid = 2 * std::min((ntiles + 1) / 2, num_sms() / 2);
       cudaError_t le = launch_clustered(tc_mlp_dgrad_kernel<true>, grid, kThreads, kSmemBytes + 1024, st, bp);
       if (le != cudaSuccess) {
         set_error("cluster launch of tc_mlp_dgrad_kernel failed: %s", cudaGetErrorString(le));
         return SPARF_ERR_CUDA;
       }
-    } else {
+      SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
+    } else if (nsplit <= 1) {
       // A operand in tensor memory (default; SPARF_TC_TMEMA=0 selects the shared-memory-operand kernel): 294 vs 360 us
-      static const bool tmem_a = !(getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '0');
       if (tmem_a) tc_mlp_dgrad_kernel<false, true><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
       else tc_mlp_dgrad_kernel<false><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
       TRACE_DUMP("dgrad");
+      SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
     }
-    SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
-
-    // 3. weight gradients: job table = (layer, slab of row tiles), ~one CTA per SM
-    WgradJobs jobs_tab;
-    WgradJob* jobs = jobs_tab.j;
-    int nj = 0;
-    auto add_jobs = [&](int tg, int tx, int mblk, int nblk, float* dW, int ldw, int col0, int enc, int slabs, float* colsum) {
-      slabs = std::max(1, std::min(slabs, ntiles));
-      for (int s = 0; s < slabs; ++s) {
-        WgradJob j;
-        j.t_g = tg; j.t_x = tx; j.mblk = mblk; j.nblk = nblk;
-        j.tile_begin = (int)((long long)ntiles * s / slabs);
-        j.tile_end = (int)((long long)ntiles * (s + 1) / slabs);
-        j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum;
-        jobs[nj++] = j;
+    if (nsplit <= 1) {
+      // fork: the leftovers run on the side stream beside the weight-gradient kernel (or everything on `st`)
+      if (side) {
+        SPARF_CHECK_CUDA(cudaEventRecord(side->fork, st));
+        SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        sd = side->stream;
       }
-    };
-    // One CTA per SM in a single wave.  A stage (32 rows of one tile) costs about the same ~2.4k clocks whatever its
-    // width (it is bound by the latency of the 3-deep HBM pipeline, profiles/r01_ncu_chain.md), so the slabs equalise
-    // the number of stages per CTA rather than bytes: 10 job types x ~14.8 slabs = 147 CTAs.
-    add_jobs(T_GHID, T_FEAT, 2, 4, grad->head_w[0], kW + kEv, 0, 0, 14, grad->head_b[0]);     // head 0, feature part
-    add_jobs(T_G7F, T_H0 + 6, 4, 4, grad->trunk_w[7] + kW, kW, 0, 0, 15, grad->trunk_b[7] + 1);  // trunk 7 rows 1..256
-    for (int l = 6; l >= 1; --l)
-      add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, 15, grad->trunk_b[l]);
-    add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, 14, nullptr);             // skip part of layer 4
-    add_jobs(t_g(0), T_ENC, 4, 1, grad->trunk_w[0], 63, 0, 1, 14, grad->trunk_b[0]);          // layer 0 (+ its bias)
-    // fork: `sd` = the side stream (or the caller's stream when overlapping is off / unavailable)
-    SideStream* side = overlap_small_kernels() ? side_stream() : nullptr;
-    cudaStream_t sd = st;
-    if (side) {
-      SPARF_CHECK_CUDA(cudaEventRecord(side->fork, st));
-      SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-      sd = side->stream;
+      rc = wgrad_launch(0, ntiles, num_sms() - 1, st);
+      if (rc) return rc;
+    } else {
+      // pipeline: dgrad(0) on every SM, then dgrad(k) on nd_sms SMs beside wgrad(k - 1) on the others (side stream),
+      // the last wgrad on every SM beside the leftovers (caller's stream)
+      for (int k = 0; k < nsplit; ++k) {
+        const int t_lo = (int)((long long)ntiles * k / nsplit), t_hi = (int)((long long)ntiles * (k + 1) / nsplit);
+        BwdParams bk = bp;
+        const long long m_off = (long long)t_lo * kTileM;
+        bk.d_sigma += m_off; bk.d_rgb += m_off * 3; bk.sigma += m_off; bk.rgb += m_off * 3;
+        bk.g_raw += m_off; bk.g_pre += m_off * 4;
+        bk.num_tiles = t_hi - t_lo;
+        bk.M = std::min<long long>(Mc - m_off, (long long)bk.num_tiles * kTileM);
+        images_advance(bk.img, t_lo);
+        const int grid = std::min(bk.num_tiles, k == 0 ? num_sms() : nd_sms);
+        tc_mlp_dgrad_kernel<false, true><<<grid, kThreads, kSmemBytes + 1024, st>>>(bk);
+        SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
+        SPARF_CHECK_CUDA(cudaEventRecord(side->sub[k], st));
+        SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->sub[k], 0));
+        rc = wgrad_launch(t_lo, t_hi, k + 1 < nsplit ? num_sms() - nd_sms : num_sms() - 1, side->stream);
+        if (rc) return rc;
+      }
     }
-    tc_mlp_wgrad_kernel<<<nj, 192, kWgSmem + 1024, st>>>(jobs_tab, img);
-    SPARF_CHECK_LAUNCH("tc_mlp_wgrad_kernel");
 
     // 4. CUDA-core leftovers: biases, density row, 128->3 head, view-direction columns
     ReduceJobs rj_tab;

@@ -114,80 +114,63 @@ class Graph(torch.nn.Module):
         return ops.raygen(pose, intr, W, ray_idx=ray_idx.to(self.device))
 
     # ---------------------------------------------------------------------------- public entry points
+    def _full_or_selected(self, opt, pose, intr, H, W, depth_range, iter, mode, pixels=None, ray_idx=None):
+        """The dispatch the three public entry points share: explicit pixels / ray indices -> one `render` call,
+        otherwise the whole image, sliced when opt.nerf.rand_rays is set (renderer.py:181-187, 236-244)."""
+        kw = dict(H=H, W=W, intr=intr, depth_range=depth_range, iter=iter, mode=mode)
+        if pixels is not None or ray_idx is not None:
+            ret = self.render(opt, pose, pixels=pixels, ray_idx=ray_idx, **kw)
+            ret.ray_idx = ray_idx
+            return ret
+        return self.render_by_slices(opt, pose, **kw) if opt.nerf.rand_rays else self.render(opt, pose, **kw)
+
+    def _train_subset(self, opt, H, W, mode, n_images):
+        """Random pixel subset shared by all rendered images in train / test-optim mode (renderer.py:114, 124), else None."""
+        if opt.nerf.rand_rays and mode in ("train", "test-optim"):
+            return torch.randperm(H * W, device=self.device)[:opt.nerf.rand_rays // n_images]
+        return None
+
     def forward(self, opt, data_dict, iter, img_idx=None, mode=None):
         """Render a random subset of pixels (train / test-optim) or all pixels of every image
         (renderer.py:77-140)."""
-        batch_size = len(data_dict.idx)
-        pose = self.get_w2c_pose(opt, data_dict, mode=mode)
         H, W = data_dict.image.shape[-2:]
-        depth_range = self._depth_range(opt, data_dict)
         if img_idx is not None:
             # (the reference passes img_idx into the `iter` slot here, renderer.py:117; no caller uses it)
-            nbr_img = len(img_idx) if isinstance(img_idx, list) else 1
-            ray_idx = None
-            if opt.nerf.rand_rays and mode in ["train", "test-optim"]:
-                ray_idx = torch.randperm(H * W, device=self.device)[:opt.nerf.rand_rays // nbr_img]
+            ray_idx = self._train_subset(opt, H, W, mode, len(img_idx) if isinstance(img_idx, list) else 1)
             ret = self.render_image_at_specific_rays(opt, data_dict, iter, img_idx=img_idx, ray_idx=ray_idx, mode=mode)
             if ray_idx is not None:
                 ret.ray_idx = ray_idx
             ret.idx_img_rendered = img_idx
             return ret
-        if opt.nerf.rand_rays and mode in ["train", "test-optim"]:
-            ray_idx = torch.randperm(H * W, device=self.device)[:opt.nerf.rand_rays // batch_size]
-            ret = self.render(opt, pose, intr=data_dict.intr, ray_idx=ray_idx, mode=mode, H=H, W=W,
-                              depth_range=depth_range, iter=iter)
-            ret.ray_idx = ray_idx
-        else:
-            ret = self.render_by_slices(opt, pose, intr=data_dict.intr, mode=mode, H=H, W=W, depth_range=depth_range,
-                                        iter=iter) if opt.nerf.rand_rays else \
-                self.render(opt, pose, intr=data_dict.intr, mode=mode, H=H, W=W, depth_range=depth_range, iter=iter)
-        ret.idx_img_rendered = torch.arange(start=0, end=batch_size, device=self.device)
+        n_images = len(data_dict.idx)
+        ray_idx = self._train_subset(opt, H, W, mode, n_images)
+        ret = self._full_or_selected(opt, self.get_w2c_pose(opt, data_dict, mode=mode), data_dict.intr, H, W,
+                                     self._depth_range(opt, data_dict), iter, mode, ray_idx=ray_idx)
+        ret.idx_img_rendered = self._arange(n_images)
         return ret
 
     def render_image_at_specific_pose_and_rays(self, opt, data_dict, pose, intr, H, W, iter, pixels=None,
                                                ray_idx=None, mode="train"):
         """Render given pixels (or the full image) at given w2c pose(s) (renderer.py:142-190)."""
-        if pose.dim() == 2:
-            pose = pose.unsqueeze(0)
-        if intr.dim() == 2:
-            intr = intr.unsqueeze(0)
-        depth_range = self._depth_range(opt, data_dict)
-        if ray_idx is None and pixels is None:
-            ret = self.render_by_slices(opt, pose, intr=intr, mode=mode, H=H, W=W, depth_range=depth_range, iter=iter) \
-                if opt.nerf.rand_rays else \
-                self.render(opt, pose, intr=intr, mode=mode, H=H, W=W, depth_range=depth_range, iter=iter)
-        else:
-            ret = self.render(opt, pose, intr=intr, pixels=pixels, ray_idx=ray_idx, mode=mode, H=H, W=W,
-                              depth_range=depth_range, iter=iter)
-            ret.ray_idx = ray_idx
-        return ret
+        pose = pose.unsqueeze(0) if pose.dim() == 2 else pose
+        intr = intr.unsqueeze(0) if intr.dim() == 2 else intr
+        return self._full_or_selected(opt, pose, intr, H, W, self._depth_range(opt, data_dict), iter, mode,
+                                      pixels=pixels, ray_idx=ray_idx)
 
     def render_image_at_specific_rays(self, opt, data_dict, iter, img_idx=None, pixels=None, ray_idx=None,
                                       mode="train"):
         """Render given pixels for all (or a subset `img_idx`) of the scene's images (renderer.py:192-248)."""
-        pose = self.get_w2c_pose(opt, data_dict, mode=mode)
-        intr = data_dict.intr
-        batch_size = pose.shape[0]
+        pose, intr = self.get_w2c_pose(opt, data_dict, mode=mode), data_dict.intr
+        n_images = pose.shape[0]
         if img_idx is not None:
-            if isinstance(img_idx, (tuple, list)):
-                pose = pose[img_idx].view(-1, 3, 4)
-                intr = intr[img_idx].view(-1, 3, 3)
-            else:
-                pose = pose[img_idx].unsqueeze(0)
-                intr = intr[img_idx].unsqueeze(0)
+            if not isinstance(img_idx, (tuple, list)):
                 img_idx = [img_idx]
+            pose, intr = pose[img_idx].view(-1, 3, 4), intr[img_idx].view(-1, 3, 3)
         H, W = data_dict.image.shape[-2:]
-        depth_range = self._depth_range(opt, data_dict)
-        if ray_idx is None and pixels is None:
-            ret = self.render_by_slices(opt, pose, intr=intr, mode=mode, H=H, W=W, depth_range=depth_range, iter=iter) \
-                if opt.nerf.rand_rays else \
-                self.render(opt, pose, intr=intr, mode=mode, H=H, W=W, depth_range=depth_range, iter=iter)
-        else:
-            ret = self.render(opt, pose, intr=intr, pixels=pixels, ray_idx=ray_idx, mode=mode, H=H, W=W,
-                              depth_range=depth_range, iter=iter)
-            ret.ray_idx = ray_idx
+        ret = self._full_or_selected(opt, pose, intr, H, W, self._depth_range(opt, data_dict), iter, mode,
+                                     pixels=pixels, ray_idx=ray_idx)
         ret.idx_img_rendered = torch.from_numpy(np.array(img_idx)).to(self.device) if img_idx is not None else \
-            self._arange(batch_size)
+            self._arange(n_images)
         return ret
 
     def _arange(self, n):
