@@ -512,6 +512,24 @@ __device__ __forceinline__ void chain_producer(const ChainSmem& s, const uint8_t
   if ((threadIdx.x & 31) == 0) trace_end(tr, 0);
 }
 
+// Same stream in 32 KB copies over stage pairs (s, s + 1): barriers of the EVEN stage only (kRingPairs).
+__device__ __forceinline__ void chain_producer_pairs(const ChainSmem& s, const uint8_t* packed, int my_tiles, int nchunks) {
+  Trace tr; trace_begin(tr);
+  const int npairs = nchunks / 2, nring = s.nstages / 2;
+  const long long total = (long long)my_tiles * npairs;
+  for (long long g = 0; g < total; ++g) {
+    const int c = (int)(g % npairs);
+    const uint32_t stage = 2u * (uint32_t)(g % nring), phase = (uint32_t)((g / nring) & 1);
+    twait(tr, 0, &s.w_empty[stage], phase ^ 1);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&s.w_full[stage], 2 * kChunkBytes);
+      bulk_g2s(s.ring + stage * kChunkBytes, packed + (size_t)c * 2 * kChunkBytes, 2 * kChunkBytes, &s.w_full[stage]);
+    }
+    __syncwarp();
+  }
+  if ((threadIdx.x & 31) == 0) trace_end(tr, 0);
+}
+
 // one (K block, N half): waits for its weight chunks and issues the MMAs of all passes.  Called by the WHOLE issuer
 // warp (uniform control flow and operands); one elected lane issues.
 __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
@@ -568,12 +586,14 @@ __device__ __forceinline__ void chain_issue_block(const ChainSmem& s, uint32_t& 
 // halves of a part sit in adjacent stages, i.e. form one [256 x 64] K-major operand, and ONE M128 x N256 MMA covers
 // them.  Half the instructions and barrier round trips per unit of tensor work (one issuer warp suffices) and
 // 96 instead of 128 B/clk of shared-memory operand fetch.
+template <bool kBig = false>
 __device__ __forceinline__ void chain_issue_pair256(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
                                                     uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, Trace& tr) {
   const uint32_t ring_addr = smem_u32(s.ring);
   for (int part = 0; part < 2; ++part) {
     long long t0 = trace_tic();
-    mbar_wait_two(&s.w_full[stage], phase, &s.w_full[stage + 1], phase);
+    if (kBig) mbar_wait(&s.w_full[stage], phase);
+    else mbar_wait_two(&s.w_full[stage], phase, &s.w_full[stage + 1], phase);
     trace_toc(tr, 2, t0);
     tc_fence_after();
     const uint64_t db0 = make_smem_desc(ring_addr) + (uint64_t)(stage * (kChunkBytes >> 4));
@@ -587,7 +607,7 @@ __device__ __forceinline__ void chain_issue_pair256(const ChainSmem& s, uint32_t
         if (part == 0) umma_ss(d_addr, dal0 + (uint64_t)(2 * ks), db, idesc, 1u);
       }
       umma_commit(&s.w_empty[stage]);
-      umma_commit(&s.w_empty[stage + 1]);
+      if (!kBig) umma_commit(&s.w_empty[stage + 1]);
     }
     __syncwarp();
     stage += 2;
@@ -598,12 +618,14 @@ __device__ __forceinline__ void chain_issue_pair256(const ChainSmem& s, uint32_t
 // Same with the A operand in tensor memory (columns a_hi_t / a_lo_t of this K block, +8 columns per K16 step): the MMA
 // fetches only B from shared memory and the epilogue hands activations over with tcgen05.st instead of swizzled
 // st.shared + fence.proxy.async.
+template <bool kBig = false>
 __device__ __forceinline__ void chain_issue_pair256_ts(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi_t,
                                                        uint32_t a_lo_t, uint32_t d_addr, uint32_t idesc, bool first_kb, Trace& tr) {
   const uint32_t ring_addr = smem_u32(s.ring);
   for (int part = 0; part < 2; ++part) {
     long long t0 = trace_tic();
-    mbar_wait_two(&s.w_full[stage], phase, &s.w_full[stage + 1], phase);
+    if (kBig) mbar_wait(&s.w_full[stage], phase);
+    else mbar_wait_two(&s.w_full[stage], phase, &s.w_full[stage + 1], phase);
     trace_toc(tr, 2, t0);
     tc_fence_after();
     // descriptor of K step ks = descriptor of the stage + 2 ks in its 16-byte start-address field (no carry: the ring
@@ -618,7 +640,7 @@ __device__ __forceinline__ void chain_issue_pair256_ts(const ChainSmem& s, uint3
         if (part == 0) umma_ts(d_addr, a_lo_t + ks * 8, db, idesc, 1u);
       }
       umma_commit(&s.w_empty[stage]);
-      umma_commit(&s.w_empty[stage + 1]);
+      if (!kBig) umma_commit(&s.w_empty[stage + 1]);
     }
     __syncwarp();
     stage += 2;
@@ -627,9 +649,32 @@ __device__ __forceinline__ void chain_issue_pair256_ts(const ChainSmem& s, uint3
 }
 
 // one [128 x 64] weight chunk per part against an A operand in tensor memory (the N = 128 colour-head layer)
+template <bool kBig = false>
 __device__ __forceinline__ void chain_issue_single_ts(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi_t,
                                                       uint32_t a_lo_t, uint32_t d_addr, uint32_t idesc, bool first_kb, Trace& tr) {
   const uint32_t ring_addr = smem_u32(s.ring);
+  if (kBig) {     // (hi, lo) parts of the chunk arrived together in the stage pair (stage, stage + 1)
+    twait(tr, 2, &s.w_full[stage], phase);
+    tc_fence_after();
+    const uint64_t db0 = make_smem_desc(ring_addr) + (uint64_t)(stage * (kChunkBytes >> 4));
+    if (elect_one()) {
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t db = db0 + (uint64_t)(part * (kChunkBytes >> 4) + 2 * ks);
+          const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
+          umma_ts(d_addr, a_hi_t + ks * 8, db, idesc, acc);
+          if (part == 0) umma_ts(d_addr, a_lo_t + ks * 8, db, idesc, 1u);
+        }
+      }
+      umma_commit(&s.w_empty[stage]);
+    }
+    __syncwarp();
+    stage += 2;
+    if (stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
+    return;
+  }
   for (int part = 0; part < 2; ++part) {
     twait(tr, 2, &s.w_full[stage], phase);
     tc_fence_after();
@@ -697,6 +742,14 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 #define SPARF_STORE_LSU 0
 #endif
 constexpr bool kStoreLsu = SPARF_STORE_LSU != 0;
+// SPARF_RING_PAIRS = 1 (TMEM-operand kernels): the weight producer moves one 32 KB [256 x 64] operand (or the
+// (hi, lo) parts of a [128 x 64] colour-head chunk) per bulk copy and mbarrier instead of two 16 KB chunks: half the
+// copy issues, expect_tx arms, barrier polls and commits per unit of tensor work (inference forward 335 -> 324 us,
+// dgrad 307 -> 302 us, taped forward unchanged).
+#ifndef SPARF_RING_PAIRS
+#define SPARF_RING_PAIRS 1
+#endif
+constexpr bool kRingPairs = SPARF_RING_PAIRS != 0;
 // LSU mode: number of store warps (1: warp 19; 2: + warp 18, the second-issuer warp the TMEM-operand kernels leave idle);
 // store warp i takes the staged blocks with running index % kStoreWarps == i
 #ifndef SPARF_STORE_WARPS
@@ -772,6 +825,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
 
   if (warp == 0) {
     if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
+    else if (kTmemA && kRingPairs) chain_producer_pairs(cs, my_packed, my_tiles, kChunksPerTile);
     else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1);
   } else if (warp == 1 || (warp == 2 + kEpiWarps && !(kTmemA && kStoreWarps == 2))) {
     const int issuer = warp == 1 ? 0 : 1;
@@ -829,15 +883,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
               if (kb_is_enc(l, kbi)) {                              // encoder block: operand in shared memory
                 if (l == 0) { twait(tr, 1, &cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
                 tc_fence_after();
-                chain_issue_pair256(cs, stage, phase, enc_addr, enc_addr + kChunkBytes, tmem_base, idesc256, kbi == 0, tr);
+                chain_issue_pair256<kRingPairs>(cs, stage, phase, enc_addr, enc_addr + kChunkBytes, tmem_base, idesc256, kbi == 0, tr);
               } else {
                 const int a = kb_act_index(l, kbi);
                 twait(tr, 1, &cs.a_ready[a], a_cnt[a] & 1);
                 ++a_cnt[a];
                 tc_fence_after();
                 const uint32_t a_hi_t = tmem_base + 256u + (uint32_t)(a * 32), a_lo_t = tmem_base + 384u + (uint32_t)(a * 32);
-                if (l == 8) chain_issue_single_ts(cs, stage, phase, a_hi_t, a_lo_t, tmem_base, idesc128, kbi == 0, tr);
-                else chain_issue_pair256_ts(cs, stage, phase, a_hi_t, a_lo_t, tmem_base, idesc256, kbi == 0, tr);
+                if (l == 8) chain_issue_single_ts<kRingPairs>(cs, stage, phase, a_hi_t, a_lo_t, tmem_base, idesc128, kbi == 0, tr);
+                else chain_issue_pair256_ts<kRingPairs>(cs, stage, phase, a_hi_t, a_lo_t, tmem_base, idesc256, kbi == 0, tr);
               }
             }
             if (elect_one()) umma_commit(&cs.d_full[0]);
@@ -1232,6 +1286,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
 
   if (warp == 0) {
     if (kPair) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false);
+    else if (kTmemA && kRingPairs) chain_producer_pairs(cs, p.packed, my_tiles, kBwdChunksPerTile);
     else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false);
   } else if (warp == 1 || (warp == 2 + kEpiWarps && !(kTmemA && kStoreWarps == 2))) {
     const int issuer = warp == 1 ? 0 : 1;
@@ -1282,7 +1337,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             ++a_cnt[kbi];
             tc_fence_after();
             if (kTmemA) {
-              chain_issue_pair256_ts(cs, stage, phase, tmem_base + 256u + (uint32_t)(kbi * 32),
+              chain_issue_pair256_ts<kRingPairs>(cs, stage, phase, tmem_base + 256u + (uint32_t)(kbi * 32),
                                      tmem_base + 384u + (uint32_t)(kbi * 32), tmem_base, idesc, kbi == 0, tr);
             } else {
               const uint32_t a_hi = act_addr + kbi * kChunkBytes, a_lo = act_addr + (4 + kbi) * kChunkBytes;
