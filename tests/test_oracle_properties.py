@@ -79,3 +79,24 @@ def test_distortion_loss_is_translation_invariant_and_quadratic(S, seed):
     assert torch.allclose(O.distortion_loss(t + 7.5, w), base, rtol=1e-9, atol=1e-12)
     assert torch.allclose(O.distortion_loss(t, 3 * w), 9 * base, rtol=1e-9, atol=1e-12)
     assert base >= 0
+
+
+# ------------------------------------------------------------------------------------------------ pose algebra (round 2)
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.floats(-1.5, 1.5, allow_nan=False, width=32), min_size=6, max_size=6))
+def test_se3_exponential_is_rigid_and_composes(v):
+    """se3_to_SE3 (camera.py:142-157 restated): R is a rotation, exp(0) = identity, and composing a pose with its inverse
+    (compose_pair, camera.py:108-115) gives the identity."""
+    wu = torch.tensor(v, dtype=torch.float64)[None]
+    P = O.se3_to_SE3(wu)[0]
+    R, t = P[:, :3], P[:, 3]
+    assert torch.allclose(R @ R.T, torch.eye(3, dtype=torch.float64), atol=1e-9)
+    assert abs(float(torch.linalg.det(R)) - 1.0) < 1e-9
+    Pinv = O.invert_pose(P[None])[0]
+    I = O.compose_pair(P[None], Pinv[None])[0]
+    assert torch.allclose(I, torch.cat([torch.eye(3, dtype=torch.float64), torch.zeros(3, 1, dtype=torch.float64)], 1), atol=1e-9)
+    Z = O.se3_to_SE3(torch.zeros(1, 6, dtype=torch.float64))[0]
+    assert torch.allclose(Z, torch.cat([torch.eye(3, dtype=torch.float64), torch.zeros(3, 1, dtype=torch.float64)], 1))
+    # translation part: for a pure translation generator (w = 0) V = I
+    wu0 = torch.cat([torch.zeros(3, dtype=torch.float64), torch.tensor(v[3:], dtype=torch.float64)])[None]
+    assert torch.allclose(O.se3_to_SE3(wu0)[0][:, 3], wu0[0, 3:], atol=1e-12)
