@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """Benchmark of the SPARF ray-marching hot path (BASELINE.json metric: rays/s, fwd+bwd, 128 samples/ray).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c2h|c3|c4|c5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c2h|c3|c4|c5] [--impl ours|reference]
                     [--engine auto|simt_fp32|tc_3x] [--graph 0|1] [--device cpu|cuda (reference arm)]
 
 One "step" = one pass of the hot path over one synthetic ray batch of a BASELINE config, through the public API
 (`Graph.render_image_at_specific_rays` + the loss module's `compute_loss` + `backward()`), gradients zeroed each step:
 
+    c1   BASELINE config 1 (the reference's own CPU-runnable case): one 32x32 view, identity pose, 256 rays x 64 samples
     c2   (default; the driver's line) DTU-shaped 3 views 300x400, fixed GT poses, 3 x 341 = 1023 rays x 128 coarse
          samples, photometric loss -- the "1024-ray / 128-sample" headline shape
     c2h  the real DTU setting of config 2: + hierarchical fine pass (128 resampled + 128 coarse = 256 through nerf_fine)
@@ -47,6 +48,10 @@ import torch
 MACS_PER_SAMPLE = 63 * 256 + 3 * 256 * 256 + 319 * 256 + 2 * 256 * 256 + 256 * 257 + 283 * 128 + 128 * 3  # 527 872
 
 CONFIGS = {
+    "c1": dict(B=1, H=32, W=32, focal=32.0, rand_rays=256, S=64, fine=False, S_fine=64, depth_range=(0.5, 2.5),
+               depth_param="metric", poses=False, c2f=None, progress=None, loss_type="photometric", scaling="weak",
+               identity=True,
+               desc="BASELINE config 1: single 32x32 synthetic view, identity pose, 256 rays x 64 coarse samples, photometric loss, fwd+bwd (the reference's CPU-runnable case)"),
     "c2": dict(B=3, H=300, W=400, focal=400.0, rand_rays=1024, S=128, fine=False, S_fine=128, depth_range=(1.2, 5.2),
                depth_param="metric", poses=False, c2f=None, progress=None, loss_type="photometric", scaling="weak",
                desc="DTU-shaped 3 views 300x400, fixed GT poses, 3x341=1023 rays x 128 coarse samples, photometric loss, fwd+bwd"),
@@ -161,7 +166,7 @@ def build_problem(cfg_name, impl, device, seed=0, stratified=True):
         opt.loss_weight.depth_cons = -3.0
     torch.manual_seed(seed)
     np.random.seed(seed)
-    data = common.make_scene(seed, B, H, W, focal=cfg["focal"])
+    data = common.make_scene(seed, B, H, W, focal=cfg["focal"], identity=cfg.get("identity", False))
     data.depth_range = torch.tensor([list(map(float, cfg.get("data_depth_range", cfg["depth_range"])))] * B)
     for k in ("image", "intr", "pose", "depth_range", "idx"):
         data[k] = data[k].to(device)
