@@ -623,7 +623,8 @@ def run_reference(args):
     line = dict(impl="reference", metric=METRIC, value=v, unit="rays/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dt * 1e3, higher_is_better=True, scaling=cfg["scaling"], vs_baseline=None,
                 dtype="fp32 (torch CPU)" if args.device != "cuda" else "fp32 (torch CUDA, TF32 off)", data="synthetic",
-                config=dict(workload=cfg["desc"], name=args.config,
+                config=dict(workload=cfg["desc"], name=args.config, rays_per_gpu=n_rays, global_rays=n_rays,
+                            samples_per_ray=cfg["S"], fine_samples_per_ray=(cfg["S"] + cfg["S_fine"]) if cfg["fine"] else 0,
                             note=("the unmodified reference (git-ignored copy oracle/_ref made by oracle/build_ref.py), its own "
                                   "Graph + loss modules" if kind == "reference" else
                                   "oracle/_ref absent: timed on the torch restatement oracle/sparf_oracle.py, pinned to the reference by tests/golden")),
