@@ -25,8 +25,9 @@
  * capturable into a CUDA graph).  A workspace must not be shared by calls running concurrently on different streams.
  * Environment knobs, read once, for A/B timing only (defaults are the measured-fastest settings):
  *   SPARF_TC_OVERLAP=0   no side stream (everything on `stream`)
- *   SPARF_TC_TMEMA=0     chain kernels with shared-memory A operands (round-1 generation)
- *   SPARF_TC_PAIRS=0|1   force the cta_group::2 CTA-pair chain kernels off / on
+ *   SPARF_TC_TMEMA=0     chain kernels with shared-memory A operands (round-1 generation; also serves the single-pass
+ *                        engine and the recompute backward)
+ *   SPARF_TC_BWD_SPLIT=n, SPARF_TC_BWD_ND=k   backward pipelined in n sub-chunks, dgrad on k SMs beside wgrad (off)
  *   SPARF_TC_WCOPIES=n   replicas of the packed forward weight stream (L2 hot-spot experiment)
  */
 #ifndef SPARF_B200_H_

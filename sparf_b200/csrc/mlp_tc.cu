@@ -14,7 +14,7 @@
 //                                 colour head (128 -> 3) and activations in fp32 on CUDA cores
 //   warp 19     image store     : bulk-copies the staged bf16 tape / gradient images from shared memory to HBM
 // Older variants stay for the shapes the TMEM kernels do not cover and for comparison: operands in shared memory with
-// two N128 issuer warps (warps 1 and 18), and CTA pairs (cta_group::2, kPair).
+// two N128 issuer warps (warps 1 and 18).
 //
 // BACKWARD (tc_mlp_backward_tape; tc_mlp_backward re-runs the forward in bf16 "save" mode first):
 //   1. the taped forward dumped every layer's A-operand image (bf16 hi | lo) and 64-bit ReLU masks,
@@ -88,7 +88,7 @@ constexpr int kOffMisc = kOffW9 + 3 * 128 * 4;           // b7[0], b9[0..2], c2f
 constexpr int kOffPart = kOffMisc + 32 * 4;              // 3 x 128 x 4 floats: partial dots of column quarters 1..3
 constexpr int kOffBar = kOffPart + 3 * 128 * 4 * 4;      // mbarriers
 constexpr int kMaxSlots = 8;                              // image staging slots (g_ready / s_free barrier pairs)
-constexpr int kNumBars = 3 * kMaxStages + 5 + 4 + 2 * kMaxSlots;
+constexpr int kNumBars = 2 * kMaxStages + 5 + 4 + 2 * kMaxSlots;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16;
 constexpr int kOffBarBwd = kOffEnc + kBwdStages * kChunkBytes;   // dgrad: barriers right after its ring
 static_assert(kOffBarBwd + kNumBars * 8 + 16 <= kSmemBytes, "dgrad shared-memory map exceeds the launch size");
@@ -368,7 +368,7 @@ struct ChainSmem {
   uint8_t* base;
   uint8_t* ring;           // nstages x 16 KB weight ring
   int nstages;
-  uint64_t *w_full, *w_empty, *a_ready, *d_full, *d_empty, *w_peer;
+  uint64_t *w_full, *w_empty, *a_ready, *d_full, *d_empty;
   uint64_t *g_ready, *s_free;   // dgrad: block j holds a finished gradient image / has been streamed out
   uint32_t* tmem_slot;
 };
@@ -384,108 +384,23 @@ __device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem, int ring_off, in
   s.a_ready = bars + 2 * kMaxStages;
   s.d_full = s.a_ready + 5;
   s.d_empty = s.d_full + 2;
-  s.w_peer = s.d_empty + 2;
-  s.g_ready = s.w_peer + kMaxStages;
+  s.g_ready = s.d_empty + 2;
   s.s_free = s.g_ready + kMaxSlots;
   s.tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   return s;
 }
 
-// ncta = 1: stand-alone CTA;  ncta = 2: CTA pair -- the leader's a_ready / d_empty collect the epilogue warps of
-// BOTH CTAs, w_peer[s] tells the leader that the peer's half of weight stage s has landed
-__device__ __forceinline__ void chain_init_barriers(const ChainSmem& s, int ncta = 1, int n_issuers = kIssuers) {
-  // w_empty: stand-alone CTA = the owning issuer's MMA commit + the other issuer's "seen it" (every waiter of a phase
-  // must gate the slot's reuse, or the ring can lap a slow waiter and its parity wait aliases); pair = the leader's commit
+__device__ __forceinline__ void chain_init_barriers(const ChainSmem& s, int n_issuers = kIssuers) {
+  // w_empty: the owning issuer's MMA commit + (two-issuer kernels) the other issuer's "seen it": every waiter of a phase
+  // must gate the slot's reuse, or the ring can lap a slow waiter and its parity wait aliases
   for (int i = 0; i < s.nstages; ++i) {
     mbar_init(&s.w_full[i], 1);
-    mbar_init(&s.w_empty[i], ncta == 1 ? n_issuers : 1);
-    mbar_init(&s.w_peer[i], 1);
+    mbar_init(&s.w_empty[i], n_issuers);
   }
-  for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps * ncta);
+  for (int i = 0; i < 5; ++i) mbar_init(&s.a_ready[i], kEpiWarps);
   for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&s.g_ready[i], kEpiWarps); mbar_init(&s.s_free[i], 1); }
-  // d_full: one commit per issuer warp (stand-alone) or the leader's multicast commit (pair)
-  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], ncta == 1 ? n_issuers : 1); mbar_init(&s.d_empty[i], kEpiWarps * ncta); }
+  for (int i = 0; i < 2; ++i) { mbar_init(&s.d_full[i], n_issuers); mbar_init(&s.d_empty[i], kEpiWarps); }   // d_full: one commit per issuer warp
   fence_barrier_init();
-}
-
-// epilogue-warp arrival on a barrier owned by the leader CTA of a pair
-template <bool kPair>
-__device__ __forceinline__ void chain_arrive(uint64_t* bar, uint32_t rank) {
-  if (!kPair || rank == 0) mbar_arrive(bar);
-  else mbar_arrive_cluster(map_to_cta(bar, 0));
-}
-
-// ---- CTA-pair variants of the producer / issuer.  Weight stream of CTA `rank`: the chunks of its N half
-// (nh = rank); the 128-wide head layer splits its single chunk into two 64-row halves.
-//   fwd chunk index = base(l) + (kbi * nh_cnt + nh) * 2 + part ;  bwd = base(bl) + (kbi * 2 + part) * 2 + nh
-__device__ __forceinline__ int fwd_chunk_base(int l) {
-  int b = 0;
-  for (int i = 0; i < l; ++i) b += layer_nkb(i) * layer_nh(i) * 2;
-  return b;
-}
-__device__ __forceinline__ int bwd_chunk_base(int bl) {
-  int b = 0;
-  for (int i = 0; i < bl; ++i) b += bwd_nkb(i) * 4;
-  return b;
-}
-
-// one WARP per CTA (uniform control flow, an elected lane issues); relay = true: the peer's second warp runs the same
-// loop in "forward the completion to the leader" mode instead of issuing copies
-template <bool kBwd>
-__device__ __forceinline__ void pair_weight_loop(const ChainSmem& s, const uint8_t* packed, int my_pairs, int passes,
-                                                 uint32_t rank, bool relay) {
-  uint32_t stage = 0, phase = 0;
-  const int nl = kBwd ? kNumBwdLayers : kNumLayers;
-  for (int it = 0; it < my_pairs; ++it) {
-    for (int l = 0; l < nl; ++l) {
-      const int nkb = kBwd ? bwd_nkb(l) : layer_nkb(l);
-      const bool half = !kBwd && l == 8;      // N = 128: 64 rows per CTA
-      const int base = kBwd ? bwd_chunk_base(l) : fwd_chunk_base(l);
-      for (int kbi = 0; kbi < nkb; ++kbi) {
-        for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
-          if (relay) {
-            mbar_wait(&s.w_full[stage], phase);
-            if (elect_one()) mbar_arrive_cluster(map_to_cta(&s.w_peer[stage], 0));
-          } else {
-            const int chunk = half ? base + kbi * 2 + part
-                                   : (kBwd ? base + (kbi * 2 + part) * 2 + (int)rank : base + (kbi * 2 + (int)rank) * 2 + part);
-            const uint32_t bytes = half ? kChunkBytes / 2 : kChunkBytes;
-            const uint8_t* src = packed + (size_t)chunk * kChunkBytes + (half ? rank * (kChunkBytes / 2) : 0);
-            mbar_wait(&s.w_empty[stage], phase ^ 1);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(&s.w_full[stage], bytes);
-              bulk_g2s(s.ring + stage * kChunkBytes, src, bytes, &s.w_full[stage]);
-            }
-          }
-          __syncwarp();
-          if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  }
-}
-
-// leader: all MMAs of one K block (both passes), M = 256 across the pair, N = `n` columns
-__device__ __forceinline__ void pair_issue_block(const ChainSmem& s, uint32_t& stage, uint32_t& phase, uint32_t a_hi,
-                                                 uint32_t a_lo, uint32_t d_addr, uint32_t idesc, bool first_kb, int passes) {
-  const uint32_t ring_addr = smem_u32(s.ring);
-  for (int part = 0; part < (passes == 1 ? 1 : 2); ++part) {
-    mbar_wait_both(&s.w_full[stage], &s.w_peer[stage], phase);
-    tc_fence_after();
-    const uint32_t b_addr = ring_addr + stage * kChunkBytes;
-    if (elect_one()) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t db = make_smem_desc(b_addr + ks * 32);
-        const uint32_t acc = (first_kb && part == 0 && ks == 0) ? 0u : 1u;
-        umma_ss2(d_addr, make_smem_desc(a_hi + ks * 32), db, idesc, acc);
-        if (part == 0 && passes != 1) umma_ss2(d_addr, make_smem_desc(a_lo + ks * 32), db, idesc, 1u);
-      }
-      umma_commit2(&s.w_empty[stage]);
-    }
-    __syncwarp();
-    if (++stage == (uint32_t)s.nstages) { stage = 0; phase ^= 1; }
-  }
 }
 
 // weight producer (warp 0, uniform control flow, an elected lane issues): streams the per-tile sequence of `nchunks`
@@ -697,11 +612,7 @@ __device__ __forceinline__ void chain_issue_single_ts(const ChainSmem& s, uint32
 // ------------------------------------------------------------------------------------------------
 // the fused forward kernel
 // ------------------------------------------------------------------------------------------------
-// kPair: launched as clusters of 2 CTAs; each CTA keeps its own 128-row tile (A operand, accumulator lanes,
-// epilogue) but the pair's leader issues ONE tcgen05.mma.cta_group::2 (M = 256) per step with the B operand
-// split across the two SMs, which halves the weight bytes every SM has to pull per unit of tensor work.
-//
-// kTmemA (stand-alone CTA, 3 passes): the A operand of every layer except the encoder block lives in tensor memory.
+// kTmemA (3 passes, fp16 halves): the A operand of every layer except the encoder block lives in tensor memory.
 //   TMEM  [0,256) ONE accumulator | [256,384) A hi | [384,512) A lo (32 columns per K block)
 //   smem  [0,32K) encoder operand (hi, lo) | taping: [32K,80K) three rotating 16 KB staging slots for the bf16 tape
 //         images + an 8-stage weight ring; inference: a 10-stage ring | bias / small weights / barriers as before
@@ -776,9 +687,8 @@ constexpr int kOffRingTInf = 2 * kChunkBytes, kStagesTInf = 10;
 static_assert(kOffRingTSave + kStagesTSave * kChunkBytes <= kOffBias && kOffRingTInf + kStagesTInf * kChunkBytes <= kOffBias,
               "tensor-memory-operand forward: shared-memory map");
 
-template <bool kF16, bool kPair, bool kTmemA = false>
+template <bool kF16, bool kTmemA = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams p) {
-  static_assert(!(kPair && kTmemA), "the TMEM-operand variant is for stand-alone CTAs");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
@@ -804,68 +714,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
     s_misc[1] = p.b9[0]; s_misc[2] = p.b9[1]; s_misc[3] = p.b9[2];
   }
   if (tid < 16) s_misc[8 + tid] = tid < kL ? band_weight(p.c2f, kL, tid) : 0.f;
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  const uint8_t* my_packed = p.packed + (size_t)((kPair ? blockIdx.x / 2 : blockIdx.x) % p.ncopies) * kChunksPerTile * kChunkBytes;
-  if (tid == 32) chain_init_barriers(cs, kPair ? 2 : 1, kTmemA ? 1 : kIssuers);
-  if (kPair) cluster_sync_all();     // barrier inits of both CTAs visible before any remote arrive / multicast commit
+  const uint8_t* my_packed = p.packed + (size_t)(blockIdx.x % p.ncopies) * kChunksPerTile * kChunkBytes;
+  if (tid == 32) chain_init_barriers(cs, kTmemA ? 1 : kIssuers);
   if (warp == 1) {
-    if (kPair) { tmem_alloc2(cs.tmem_slot, 512); tmem_relinquish2(); }
-    else { tmem_alloc(cs.tmem_slot, 512); tmem_relinquish(); }
+    tmem_alloc(cs.tmem_slot, 512);
+    tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *cs.tmem_slot, 0);   // warp-uniform for the compiler
 
-  // work items: tiles (stand-alone) or tile pairs (CTA pair: tile = 2 * pair + rank; a missing odd tile is a dummy)
-  const int n_items = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
-  const int n_workers = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
-  const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
-  const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles b, b + grid, ...
 
   if (warp == 0) {
-    if (kPair) pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, false);
-    else if (kTmemA && kRingPairs) chain_producer_pairs(cs, my_packed, my_tiles, kChunksPerTile);
+    if (kTmemA && kRingPairs) chain_producer_pairs(cs, my_packed, my_tiles, kChunksPerTile);
     else chain_producer(cs, my_packed, my_tiles, kChunksPerTile, p.passes == 1);
   } else if (warp == 1 || (warp == 2 + kEpiWarps && !(kTmemA && kStoreWarps == 2))) {
     const int issuer = warp == 1 ? 0 : 1;
     // ============================== MMA issuer ==============================
-    if (kPair && issuer != 0) {
-      // the second issuer warp has no role in a CTA pair
-    } else if (kPair && rank == 1) {
-      pair_weight_loop<false>(cs, my_packed, my_tiles, p.passes, rank, true);   // relay "my half landed" to the leader
-    } else if (kPair) {
-      const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
-      uint32_t stage = 0, phase = 0;
-      uint32_t a_cnt[5] = {0, 0, 0, 0, 0};
-      uint32_t d_cnt[2] = {0, 0};
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int l = 0; l < kNumLayers; ++l) {
-          const int buf = l & 1;
-          const uint32_t idesc = make_idesc(256, l == 8 ? 128 : 256, kF16 ? 0 : 1);
-          mbar_wait_cluster(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
-          ++d_cnt[buf];
-          tc_fence_after();
-          const int nkb = layer_nkb(l);
-          for (int kbi = 0; kbi < nkb; ++kbi) {
-            uint32_t a_hi, a_lo;
-            if (kb_is_enc(l, kbi)) {
-              if (l == 0) { mbar_wait_cluster(&cs.a_ready[4], a_cnt[4] & 1); ++a_cnt[4]; }
-              a_hi = enc_addr; a_lo = enc_addr + kChunkBytes;
-            } else {
-              int a = kb_act_index(l, kbi);
-              mbar_wait_cluster(&cs.a_ready[a], a_cnt[a] & 1);
-              ++a_cnt[a];
-              a_hi = act_addr + a * kChunkBytes; a_lo = act_addr + (4 + a) * kChunkBytes;
-            }
-            tc_fence_after();
-            pair_issue_block(cs, stage, phase, a_hi, a_lo, tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, p.passes);
-          }
-          if (elect_one()) umma_commit2(&cs.d_full[buf]);
-          __syncwarp();
-        }
-      }
-    } else if (kTmemA) {
+    if (kTmemA) {
       if (issuer == 0) {
         const uint32_t idesc256 = make_idesc(128, 256, kF16 ? 0 : 1), idesc128 = make_idesc(128, 128, kF16 ? 0 : 1);
         const uint32_t enc_addr = smem_u32(enc_blk);
@@ -900,7 +768,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
         }
         if (lane == 0) trace_end(tr, 1);
       }
-    } else if (!kPair) {
+    } else {
       const uint32_t idesc = make_idesc(128, 128, kF16 ? 0 : 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct), enc_addr = smem_u32(smem + kOffEnc);
       uint32_t stage = 0, phase = 0;
@@ -987,12 +855,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
     Trace tr; trace_begin(tr);
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
-      const bool tile_ok = tile < p.num_tiles;                       // false only for the dummy half of an odd pair
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const long long m = (long long)tile * kTileM + row;
-      const bool valid = tile_ok && m < p.M;
+      const bool valid = m < p.M;
       const long long ray = valid ? m / p.S : 0;
-      const bool save = p.save && tile_ok;
+      const bool save = p.save != 0;
 
       // ---------------- positional encoding -> A_enc (internal column order: x y z 0 | (sin,cos) pairs)
       {
@@ -1022,9 +889,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
         Split16 sp;
         split16<kF16>(vals, sp);
         store16(sp, row, cq * kEpiCols, enc_blk, enc_blk + kChunkBytes);
-        if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+        fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) chain_arrive<kPair>(&cs.a_ready[4], rank);
+        if (lane == 0) mbar_arrive(&cs.a_ready[4]);
         if (save) {
           if (kF16) split16<false>(vals, sp);
           store16_image(sp, row, cq * kEpiCols, p.img.at(T_ENC, tile, 0, 0), p.img.at(T_ENC, tile, 0, 1));
@@ -1188,9 +1055,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
           } else {
             split16<kF16>(f, sp);
             store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
-            if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) chain_arrive<kPair>(&cs.a_ready[j], rank);
+            if (lane == 0) mbar_arrive(&cs.a_ready[j]);
             if (save) {
               const int tsave = l == 7 ? T_FEAT : T_H0 + l;
               if (kF16) split16<false>(f, sp);
@@ -1203,7 +1070,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
         if (!kTmemA) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
+          if (lane == 0) mbar_arrive(&cs.d_empty[buf]);
         }
         if (save) *p.img.mask_at(tile, l, row, cq) = make_uint2(mbits[0], mbits[1]);
 
@@ -1240,21 +1107,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (kPair) cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still signal it
-  if (warp == 1) {
-    if (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
-  }
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
 // the fused input-gradient (dgrad) kernel: dL/dz chain from the colour head to layer 0
 // ------------------------------------------------------------------------------------------------
-// kTmemA (stand-alone CTA only): TMEM = [0,256) ONE accumulator | [256,384) A hi | [384,512) A lo (32 columns per K block).
+// kTmemA: TMEM = [0,256) ONE accumulator | [256,384) A hi | [384,512) A lo (32 columns per K block).
 // The epilogue loads its whole share of the accumulator into registers first and hands the accumulator back at once,
 // so a single accumulator still lets layer l+1's MMAs overlap layer l's epilogue.
-template <bool kPair, bool kTmemA = false>
+template <bool kTmemA>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdParams p) {
-  static_assert(!(kPair && kTmemA), "the TMEM-operand variant is for stand-alone CTAs");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // shared-memory map of this kernel: activations (8 blocks) | 6-stage weight ring | barriers.  The density row and the
@@ -1268,57 +1131,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
                               : chain_carve(smem, kOffEnc, kBwdStages, kOffBarBwd);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
-  if (tid == 32) chain_init_barriers(cs, kPair ? 2 : 1, 1);   // stand-alone: ONE issuer warp (N = 256 MMAs)
-  if (kPair) cluster_sync_all();
+  if (tid == 32) chain_init_barriers(cs, 1);   // ONE issuer warp (N = 256 MMAs)
   if (warp == 1) {
-    if (kPair) { tmem_alloc2(cs.tmem_slot, 512); tmem_relinquish2(); }
-    else { tmem_alloc(cs.tmem_slot, 512); tmem_relinquish(); }
+    tmem_alloc(cs.tmem_slot, 512);
+    tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *cs.tmem_slot, 0);
-  const int n_items = kPair ? (p.num_tiles + 1) / 2 : p.num_tiles;
-  const int n_workers = kPair ? (int)gridDim.x / 2 : (int)gridDim.x;
-  const int worker = kPair ? (int)blockIdx.x / 2 : (int)blockIdx.x;
-  const int my_tiles = (n_items - worker + n_workers - 1) / n_workers;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
-    if (kPair) pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, false);
-    else if (kTmemA && kRingPairs) chain_producer_pairs(cs, p.packed, my_tiles, kBwdChunksPerTile);
+    if (kTmemA && kRingPairs) chain_producer_pairs(cs, p.packed, my_tiles, kBwdChunksPerTile);
     else chain_producer(cs, p.packed, my_tiles, kBwdChunksPerTile, false);
   } else if (warp == 1 || (warp == 2 + kEpiWarps && !(kTmemA && kStoreWarps == 2))) {
     const int issuer = warp == 1 ? 0 : 1;
-    if (kPair && issuer != 0) {
-      // the second issuer warp has no role in a CTA pair
-    } else if (kPair && rank == 1) {
-      pair_weight_loop<true>(cs, p.packed, my_tiles, 3, rank, true);
-    } else if (kPair) {
-      const uint32_t idesc = make_idesc(256, 256, 1);
-      const uint32_t act_addr = smem_u32(smem + kOffAct);
-      uint32_t stage = 0, phase = 0;
-      uint32_t a_cnt[4] = {0, 0, 0, 0};
-      uint32_t d_cnt[2] = {0, 0};
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int bl = 0; bl < kNumBwdLayers; ++bl) {
-          const int buf = bl & 1;
-          mbar_wait_cluster(&cs.d_empty[buf], (d_cnt[buf] & 1) ^ 1);
-          ++d_cnt[buf];
-          tc_fence_after();
-          const int nkb = bwd_nkb(bl);
-          for (int kbi = 0; kbi < nkb; ++kbi) {
-            mbar_wait_cluster(&cs.a_ready[kbi], a_cnt[kbi] & 1);
-            ++a_cnt[kbi];
-            tc_fence_after();
-            pair_issue_block(cs, stage, phase, act_addr + kbi * kChunkBytes, act_addr + (4 + kbi) * kChunkBytes,
-                             tmem_base + (uint32_t)(buf * 256), idesc, kbi == 0, 3);
-          }
-          if (elect_one()) umma_commit2(&cs.d_full[buf]);
-          __syncwarp();
-        }
-      }
-    } else if (!kPair && issuer == 0) {
+    if (issuer == 0) {
       const uint32_t idesc = make_idesc(128, 256, 1);
       const uint32_t act_addr = smem_u32(smem + kOffAct);
       uint32_t stage = 0, phase = 0;
@@ -1357,7 +1186,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
     uint8_t* act_hi = smem + kOffAct;
     uint8_t* act_lo = smem + kOffAct + 4 * kChunkBytes;
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const bool tile_ok = tile < p.num_tiles;
       for (int step = 0; step <= kNumBwdLayers; ++step) {          // step 0 = head (blocks 0, 1), step bl + 1 = layer bl
         const int nblk = step == 0 ? 2 : 4;
@@ -1413,9 +1242,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
     Trace tr; trace_begin(tr);
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile_raw = kPair ? 2 * (worker + it * n_workers) + (int)rank : (int)blockIdx.x + it * (int)gridDim.x;
-      const bool tile_ok = tile_raw < p.num_tiles;                   // false only for the dummy half of an odd pair
-      const int tile = tile_ok ? tile_raw : 0;                       // dummy: read tile 0's images, write nothing
+      const int tile_raw = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool tile_ok = true;
+      const int tile = tile_raw;
       const long long m = (long long)tile_raw * kTileM + row;
       const bool valid = tile_ok && m < p.M;
 
@@ -1470,9 +1299,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
           const uint32_t n = 9u * (uint32_t)it;
           if (n > 0) mbar_wait(&cs.s_free[j], (n - 1) & 1);
           store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
-          if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+          fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) { chain_arrive<kPair>(&cs.a_ready[j], rank); mbar_arrive(&cs.g_ready[j]); }
+          if (lane == 0) { mbar_arrive(&cs.a_ready[j]); mbar_arrive(&cs.g_ready[j]); }
         }
       }
 
@@ -1549,10 +1378,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             if (n > 0) mbar_wait(&cs.s_free[j], (n - 1) & 1);
             trace_toc(tr, 3, tt3);
             store16(sp, row, cq * kEpiCols, act_hi + (size_t)j * kChunkBytes, act_lo + (size_t)j * kChunkBytes);
-            if (kPair) fence_proxy_async_all(); else fence_proxy_async_smem();
+            fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              if (chain) chain_arrive<kPair>(&cs.a_ready[j], rank);
+              if (chain) mbar_arrive(&cs.a_ready[j]);
               mbar_arrive(&cs.g_ready[j]);
             }
           }
@@ -1560,7 +1389,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
         if (!kTmemA) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) chain_arrive<kPair>(&cs.d_empty[buf], rank);
+          if (lane == 0) mbar_arrive(&cs.d_empty[buf]);
         }
       }
     }
@@ -1568,10 +1397,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
   }
   tc_fence_before();
   __syncthreads();
-  if (kPair) cluster_sync_all();
-  if (warp == 1) {
-    if (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
-  }
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2209,32 +2035,13 @@ static int weight_copies() {
   return v;
 }
 
-// CTA-pair (cta_group::2) variants of the chain kernels.  Measured on the bench shape (profiles/r01_notes.md): the
-// inference forward is ~11% faster as pairs (half the weight bytes and operand-fetch bandwidth per SM), the taped
-// forward and the dgrad chain are slower (every epilogue hand-off becomes a cluster-scope arrive on the leader).
-// They now only serve the shapes the tensor-memory-operand kernel does not (single-pass engine, bf16 recompute);
-// SPARF_TC_PAIRS=0 / 1 forces them off / on everywhere.
-static int cta_pairs_mode() {
-  static int v = -2;
-  if (v == -2) {
-    const char* e = getenv("SPARF_TC_PAIRS");
-    v = e ? (e[0] == '1' ? 1 : 0) : -1;
-  }
-  return v;
-}
-static bool use_cta_pairs(bool inference) {
-  const int m = cta_pairs_mode();
-  return m < 0 ? inference : m == 1;
-}
-
-// which forward kernel serves a call: 0 = stand-alone CTAs with shared-memory operands, 1 = CTA pairs,
-// 2 = stand-alone CTAs with the A operand in tensor memory (fp16 3-pass only; SPARF_TC_TMEMA=0 disables it)
-enum { FWD_SMEM = 0, FWD_PAIRS = 1, FWD_TMEM = 2 };
+// which forward kernel serves a call: FWD_TMEM = the A operand in tensor memory (fp16 3-pass: every default call;
+// SPARF_TC_TMEMA=0 disables it), FWD_SMEM = operands in shared memory (single-pass engine, bf16 recompute forward)
+enum { FWD_SMEM = 0, FWD_TMEM = 2 };
 static int fwd_variant(bool f16, int passes, bool save, int num_tiles) {
   static const bool tmem_ok = !(getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '0');
-  if (tmem_ok && f16 && passes == 3 && cta_pairs_mode() != 1) return FWD_TMEM;   // 317 us inference / 425 us taped
-  if (use_cta_pairs(!save) && num_tiles >= 2) return FWD_PAIRS;
-  return FWD_SMEM;
+  (void)save; (void)num_tiles;
+  return (tmem_ok && f16 && passes == 3) ? FWD_TMEM : FWD_SMEM;
 }
 
 #ifdef SPARF_TC_TRACE
@@ -2267,23 +2074,6 @@ static void trace_dump(const char* what) {
 #define TRACE_DUMP(what) ((void)0)
 #endif
 
-template <typename K, typename P>
-static cudaError_t launch_clustered(K kernel, int grid, int block, size_t smem, cudaStream_t st, const P& params) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, params);
-}
-
 static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int S, const float* origins, const float* dirs,
                           const float* t, const float* noise, float* sigma, float* rgb, const uint8_t* packed,
                           const float* raybias, const Images* img, cudaStream_t st, int ncopies = 1) {
@@ -2302,7 +2092,6 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
   p.num_tiles = (int)((p.M + kTileM - 1) / kTileM);
   p.passes = passes;
   p.ncopies = ncopies;
-  cudaError_t rc_launch = cudaSuccess;
   p.save = img != nullptr;
   if (img) p.img = *img; else { for (int i = 0; i < T_COUNT; ++i) p.img.ptr[i] = nullptr; }
   static bool attr_set_dev[64] = {};
@@ -2311,30 +2100,18 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
   bool& attr_set = attr_set_dev[dev_ord & 63];   // function attributes are per device
   if (!attr_set) {
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
-    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
-    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
-    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
-    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_encgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEgSmem + 1024));
     attr_set = true;
   }
   const int variant = fwd_variant(f16, passes, p.save != 0, p.num_tiles);
   if (variant == FWD_TMEM) {
-    tc_mlp_fwd_kernel<true, false, true><<<std::min(p.num_tiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(p);
+    tc_mlp_fwd_kernel<true, true><<<std::min(p.num_tiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(p);
     TRACE_DUMP(p.save ? "forward (tape, A in TMEM)" : "forward f16 (A in TMEM)");
-  } else if (variant == FWD_PAIRS) {
-    const int pairs = (p.num_tiles + 1) / 2;
-    const int grid = 2 * std::min(pairs, num_sms() / 2);
-    rc_launch = f16 ? launch_clustered(tc_mlp_fwd_kernel<true, true>, grid, kThreads, kSmemBytes + 1024, st, p)
-                    : launch_clustered(tc_mlp_fwd_kernel<false, true>, grid, kThreads, kSmemBytes + 1024, st, p);
-    if (rc_launch != cudaSuccess) {
-      set_error("cluster launch of tc_mlp_fwd_kernel failed: %s", cudaGetErrorString(rc_launch));
-      return SPARF_ERR_CUDA;
-    }
   } else {
     int grid = std::min(p.num_tiles, num_sms());
     if (f16) tc_mlp_fwd_kernel<true, false><<<grid, kThreads, kSmemBytes + 1024, st>>>(p);
@@ -2585,10 +2362,9 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     bp.w7 = mlp->trunk_w[7]; bp.w9 = mlp->head_w[1];
     bp.M = Mc; bp.num_tiles = ntiles; bp.img = img;
     static const bool tmem_a = !(getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '0');
-    const bool pairs = use_cta_pairs(false) && ntiles >= 2;
     SideStream* side = overlap_small_kernels() ? side_stream() : nullptr;
-    // sub-chunk pipeline only with the stand-alone TMEM-operand chain kernel and when every sub-chunk still fills the GPU
-    int nsplit = (side && tmem_a && !pairs) ? std::min(8, std::max(1, bwd_split_env("SPARF_TC_BWD_SPLIT", kBwdSplitDefault))) : 1;
+    // sub-chunk pipeline only with the TMEM-operand chain kernel and when every sub-chunk still fills the GPU
+    int nsplit = (side && tmem_a) ? std::min(8, std::max(1, bwd_split_env("SPARF_TC_BWD_SPLIT", kBwdSplitDefault))) : 1;
     while (nsplit > 1 && ntiles / nsplit < num_sms()) --nsplit;
     const int nd_sms = std::max(16, std::min(num_sms() - 16, bwd_split_env("SPARF_TC_BWD_ND", kBwdNdDefault)));
 
@@ -2627,17 +2403,9 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     };
 
     cudaStream_t sd = st;      // stream of the CUDA-core leftovers (step 4)
-    if (pairs) {
-      const int grid = 2 * std::min((ntiles + 1) / 2, num_sms() / 2);
-      cudaError_t le = launch_clustered(tc_mlp_dgrad_kernel<true>, grid, kThreads, kSmemBytes + 1024, st, bp);
-      if (le != cudaSuccess) {
-        set_error("cluster launch of tc_mlp_dgrad_kernel failed: %s", cudaGetErrorString(le));
-        return SPARF_ERR_CUDA;
-      }
-      SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
-    } else if (nsplit <= 1) {
+    if (nsplit <= 1) {
       // A operand in tensor memory (default; SPARF_TC_TMEMA=0 selects the shared-memory-operand kernel): 294 vs 360 us
-      if (tmem_a) tc_mlp_dgrad_kernel<false, true><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
+      if (tmem_a) tc_mlp_dgrad_kernel<true><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
       else tc_mlp_dgrad_kernel<false><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
       TRACE_DUMP("dgrad");
       SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
@@ -2664,7 +2432,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
         bk.M = std::min<long long>(Mc - m_off, (long long)bk.num_tiles * kTileM);
         images_advance(bk.img, t_lo);
         const int grid = std::min(bk.num_tiles, k == 0 ? num_sms() : nd_sms);
-        tc_mlp_dgrad_kernel<false, true><<<grid, kThreads, kSmemBytes + 1024, st>>>(bk);
+        tc_mlp_dgrad_kernel<true><<<grid, kThreads, kSmemBytes + 1024, st>>>(bk);
         SPARF_CHECK_LAUNCH("tc_mlp_dgrad_kernel");
         SPARF_CHECK_CUDA(cudaEventRecord(side->sub[k], st));
         SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->sub[k], 0));

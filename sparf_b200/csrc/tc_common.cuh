@@ -84,97 +84,8 @@ __device__ __forceinline__ void mbar_wait_two(uint64_t* bar_a, uint32_t parity_a
   }
 }
 
-// ---------------------------------------------------------------------------------------------- CTA pairs
-// (thread-block cluster of 2, tcgen05 cta_group::2: one MMA spans both SMs, each SM holds half of B)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `local` as seen in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t map_to_cta(const void* local, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// wait on a LOCAL barrier that also receives arrivals from the peer CTA (cluster-scope acquire)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (++spins > (1u << 26)) {
-      printf("sparf tc: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
-    }
-  }
-}
-// wait on two LOCAL barriers of the same parity at once (own weights landed + peer's "landed" relay): both polls are
-// in flight together, so the pair costs one barrier round trip instead of two
-__device__ __forceinline__ void mbar_wait_both(uint64_t* bar_cta, uint64_t* bar_cluster, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %3;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 q, [%2], %3;\n\t"
-        "and.pred p, p, q;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar_cta)), "r"(smem_u32(bar_cluster)), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (++spins > (1u << 26)) {
-      printf("sparf tc: paired mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {   // same warp id in both CTAs
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem of both CTAs] (+)= A * B^T with M = 256 (128 rows per CTA), B rows split across the two CTAs; leader only
-__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on the barrier at the same offset in BOTH CTAs once the pair's previously issued MMAs have completed
-__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-               : "memory");
-}
-
 // generic-proxy writes (st.shared) -> visible to the async proxy (tensor core / bulk copy)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// same, when the reader is a tensor-core instruction issued by the PEER CTA of the pair
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------- bulk copy
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (complete_tx::bytes).

@@ -22,7 +22,7 @@ def test_cold_l2_repetitions_are_reproducible(monkeypatch, capsys):
 # larger than one backward chunk (chunked tape walk with accumulating gradients)
 VARIANTS = [
     ("shared-memory-operand chain kernels", {"SPARF_TC_TMEMA": "0"}, ["25"]),
-    ("CTA-pair chain kernels", {"SPARF_TC_PAIRS": "1"}, ["25"]),
+    ("backward pipelined in 3 sub-chunks", {"SPARF_TC_BWD_SPLIT": "3"}, ["25"]),
     ("no side stream", {"SPARF_TC_OVERLAP": "0"}, ["25"]),
     ("recompute backward (no tape)", {"STRESS_TAPE": "0"}, ["25"]),
     ("two backward chunks", {}, ["15", "1100", "128"]),
