@@ -199,6 +199,16 @@ int sparf_huber2_fwd_bwd(int64_t n, const float* pred, const float* target, floa
  * from base_losses.py:166-172; default off in the reference's configs): loss += scale * mean over rays; d_w [R,S] and,
  * if not NULL, d_t [R,S] are WRITTEN with scale * dLoss/d.  O(S) per ray (prefix sums over the monotone mid-points)
  * instead of the reference's [S-1, S-1] matrix. */
+/* ---------------------------------------------------------------- stand-alone positional encoding
+ * FrequencyEmbedder.__call__ + the BARF mask of NeRF.positional_encoding (frequency_nerf.py:47-69, 229-258) as a tensor
+ * op: x [n, channels] -> out [n, 2 * channels * L] (per channel L sines then L cosines, f_j = 2^j pi, times the c2f
+ * weight when use_c2f).  The MLP entry points fuse this; it exists so that the mirrored methods work on their own.
+ * Backward: d_out -> d_x [n, channels] (written). */
+int sparf_posenc_forward(int64_t n, int32_t channels, int32_t L, const float* x, int32_t use_c2f, float c2f_start,
+                         float c2f_range, const float* progress, float* out, sparf_stream_t stream);
+int sparf_posenc_backward(int64_t n, int32_t channels, int32_t L, const float* x, int32_t use_c2f, float c2f_start,
+                          float c2f_range, const float* progress, const float* d_out, float* d_x, sparf_stream_t stream);
+
 int sparf_distortion_fwd_bwd(int32_t R, int32_t S, const float* t, const float* w, float scale, float* loss,
                              float* d_w, float* d_t, sparf_stream_t stream);
 

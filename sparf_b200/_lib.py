@@ -54,6 +54,8 @@ _SIGNATURES = {
     "sparf_composite_forward": (c_int32, [c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sparf_composite_backward": (c_int32, [c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sparf_huber2_fwd_bwd": (c_int32, [c_int64, _P, _P, c_float, _P, _P, _P]),
+    "sparf_posenc_forward": (c_int32, [c_int64, c_int32, c_int32, _P, c_int32, c_float, c_float, _P, _P, _P]),
+    "sparf_posenc_backward": (c_int32, [c_int64, c_int32, c_int32, _P, c_int32, c_float, c_float, _P, _P, _P, _P]),
     "sparf_distortion_fwd_bwd": (c_int32, [c_int32, c_int32, _P, _P, c_float, _P, _P, _P, _P]),
     "sparf_adam_step": (c_int32, [c_int64, _P, _P, _P, _P, _P, _P] + [ctypes.c_double] * 7 + [_P]),
     "sparf_tc_selftest": (c_int32, [_P, _P, c_int32, _P, _P, _P]),

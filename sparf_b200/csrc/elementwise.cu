@@ -408,6 +408,65 @@ __global__ void huber2_kernel(long long n, const float* __restrict__ pred, const
 
 using namespace sparf;
 
+namespace sparf {
+// ------------------------------------------------------------------------------------------------
+// stand-alone positional encoding (FrequencyEmbedder.__call__ + NeRF.positional_encoding, frequency_nerf.py:47-69,
+// 229-258): out[n][c*2L + {0, L} + j] = w_j * {sin, cos}(x[n][c] * 2^j pi).  The MLP kernels fuse this; the tensor op
+// exists so that the mirrored methods are callable on their own.
+// ------------------------------------------------------------------------------------------------
+__global__ void posenc_fwd_kernel(long long n, int C, int L, const float* __restrict__ x, C2F c2f, float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int width = 2 * C * L;
+  if (idx >= n * width) return;
+  const int col = (int)(idx % width);
+  const long long row = idx / width;
+  const int c = col / (2 * L), rem = col - c * 2 * L, is_cos = rem >= L, j = rem - is_cos * L;
+  const float arg = mul_rn(x[row * C + c], band_freq(j));
+  out[idx] = mul_rn(is_cos ? cosf(arg) : sinf(arg), band_weight(c2f, L, j));
+}
+
+// d_x[n][c] = sum_j f_j w_j (g_sin cos(arg) - g_cos sin(arg))
+__global__ void posenc_bwd_kernel2(long long n, int C, int L, const float* __restrict__ x, C2F c2f,
+                                   const float* __restrict__ g_out, float* __restrict__ d_x) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * C) return;
+  const int c = (int)(idx % C);
+  const long long row = idx / C;
+  const float* g = g_out + row * 2 * C * L + c * 2 * L;
+  float acc = 0.f;
+  for (int j = 0; j < L; ++j) {
+    const float f = band_freq(j), arg = mul_rn(x[idx], f);
+    acc += f * band_weight(c2f, L, j) * (g[j] * cosf(arg) - g[L + j] * sinf(arg));
+  }
+  d_x[idx] = acc;
+}
+
+}  // namespace sparf
+using namespace sparf;
+
+extern "C" int sparf_posenc_forward(int64_t n, int32_t channels, int32_t L, const float* x, int32_t use_c2f, float c2f_start,
+                                    float c2f_range, const float* progress, float* out, sparf_stream_t stream) {
+  SPARF_REQUIRE(n >= 0 && channels > 0 && L > 0 && L <= 16, "posenc: bad sizes n=%lld C=%d L=%d", (long long)n, channels, L);
+  if (n == 0) return SPARF_OK;
+  C2F c2f{use_c2f, c2f_start, c2f_range, progress};
+  const long long total = n * 2 * channels * L;
+  posenc_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, channels, L, x, c2f, out);
+  SPARF_CHECK_LAUNCH("posenc_fwd_kernel");
+  return SPARF_OK;
+}
+
+extern "C" int sparf_posenc_backward(int64_t n, int32_t channels, int32_t L, const float* x, int32_t use_c2f, float c2f_start,
+                                     float c2f_range, const float* progress, const float* d_out, float* d_x,
+                                     sparf_stream_t stream) {
+  SPARF_REQUIRE(n >= 0 && channels > 0 && L > 0 && L <= 16, "posenc: bad sizes n=%lld C=%d L=%d", (long long)n, channels, L);
+  if (n == 0) return SPARF_OK;
+  C2F c2f{use_c2f, c2f_start, c2f_range, progress};
+  const long long total = n * channels;
+  posenc_bwd_kernel2<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, channels, L, x, c2f, d_out, d_x);
+  SPARF_CHECK_LAUNCH("posenc_bwd_kernel2");
+  return SPARF_OK;
+}
+
 extern "C" int sparf_raygen_forward(int32_t B, int32_t n, int32_t W, const float* pose_w2c, const float* intr_inv,
                                     const int64_t* ray_idx, const float* pixels, int32_t per_image,
                                     float* origins, float* dirs, sparf_stream_t stream) {

@@ -27,8 +27,10 @@ class FrequencyEmbedder:
             raise NotImplementedError("sparf_b200 kernels implement the log-sampled, pi-scaled encoding "
                                       "(arch.posenc.log_sampling=True, include_pi_in_posenc=True) only")
 
-    def __call__(self, opt, input, L):  # pragma: no cover - not on the kernel path
-        raise NotImplementedError("positional encoding is evaluated inside the sparf_b200 MLP kernels")
+    def __call__(self, opt, input, L):
+        """[..., C] -> [..., 2*C*L] (frequency_nerf.py:47-69).  The render path never calls this (the MLP kernels
+        fuse the encoding); it is the stand-alone tensor op for other callers."""
+        return ops.posenc(input, L)
 
 
 def _layer_dims(layers):
@@ -152,8 +154,10 @@ class NeRF(nn.Module):
                                      progress=self.progress)
         return dict(rgb_samples=rgb.view(B, N, S, 3), density_samples=sigma.view(B, N, S))
 
-    def positional_encoding(self, opt, input, embedder_fn, L):  # pragma: no cover
-        raise NotImplementedError("fused into the sparf_b200 MLP kernels (csrc/): not exposed as a tensor op")
+    def positional_encoding(self, opt, input, embedder_fn, L):
+        """Encoding with the BARF coarse-to-fine mask (frequency_nerf.py:229-258) as a stand-alone tensor op; `embedder_fn`
+        is accepted for signature compatibility (the kernel implements the log-sampled, pi-scaled embedder)."""
+        return ops.posenc(input, L, barf_c2f=opt.barf_c2f, progress=self.progress)
 
     def compute_raw_density(self, opt, points_3D_samples, embedder_pts):  # pragma: no cover
         raise NotImplementedError("fused into the sparf_b200 MLP kernels (csrc/): use forward()/forward_samples()")

@@ -462,6 +462,44 @@ def huber2(pred, target):
 
 
 # ------------------------------------------------------------------------------------------------
+# stand-alone positional encoding (the MLP kernels fuse it; this is the tensor-level op)
+# ------------------------------------------------------------------------------------------------
+class PosEncFunction(torch.autograd.Function):
+    @staticmethod
+    @_on_tensor_device
+    def forward(ctx, x, L: int, barf_c2f, progress):
+        lib = _lib.lib()
+        x_c = _f32c(x)
+        C = x_c.shape[-1]
+        n = x_c.numel() // C
+        out = torch.empty(*x_c.shape[:-1], 2 * C * L, device=x_c.device, dtype=torch.float32)
+        use = barf_c2f is not None
+        start, rng = (float(barf_c2f[0]), float(barf_c2f[1] - barf_c2f[0])) if use else (0.0, 1.0)
+        prog = _f32c(progress.detach()).reshape(1) if use else None
+        check(lib.sparf_posenc_forward(n, C, int(L), _ptr(x_c), int(use), start, rng, _ptr(prog), _ptr(out), _stream()), "posenc_forward")
+        ctx.args = (n, C, int(L), use, start, rng)
+        ctx.save_for_backward(x_c, prog if use else torch.empty(0))
+        return out
+
+    @staticmethod
+    @_on_tensor_device
+    def backward(ctx, g):
+        lib = _lib.lib()
+        x_c, prog = ctx.saved_tensors
+        n, C, L, use, start, rng = ctx.args
+        d_x = torch.empty_like(x_c)
+        check(lib.sparf_posenc_backward(n, C, L, _ptr(x_c), int(use), start, rng, _ptr(prog if use else None), _ptr(_f32c(g)),
+                                        _ptr(d_x), _stream()), "posenc_backward")
+        return d_x, None, None, None
+
+
+def posenc(x, L: int, barf_c2f=None, progress=None):
+    """[..., C] -> [..., 2*C*L]: per channel L sines then L cosines of x * 2^j * pi, times the BARF coarse-to-fine weight of
+    band j when barf_c2f = (start, end) is given (frequency_nerf.py:47-69, 248-257).  Differentiable w.r.t. x."""
+    return PosEncFunction.apply(x, L, tuple(barf_c2f) if barf_c2f is not None else None, progress)
+
+
+# ------------------------------------------------------------------------------------------------
 # distortion regulariser (default off in the reference's configs)
 # ------------------------------------------------------------------------------------------------
 class DistortionFunction(torch.autograd.Function):

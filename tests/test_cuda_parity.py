@@ -293,3 +293,31 @@ def test_gradcheck_composite_fp32_vs_autograd():
     loss_of(ref["rgb"][0], ref["depth"][0, :, 0], ref["opacity"][0, :, 0], ref["weights"][0, :, :, 0]).backward()
     for gk, rk in zip(got, [sigma.grad, rgb.grad, dirs.grad]):
         assert rel_err(gk, rk) < 2e-5
+
+
+@pytest.mark.parametrize("c2f", [None, (0.1, 0.5)])
+def test_standalone_posenc_matches_oracle(c2f):
+    """FrequencyEmbedder.__call__ / NeRF.positional_encoding as tensor ops (sparf_posenc_forward / _backward) vs the
+    oracle's restatement of frequency_nerf.py:47-69, 248-257: values to fp32 rounding of sin / cos at arguments up to
+    2^9 pi x, gradient w.r.t. the input vs autograd through the oracle formula in fp64."""
+    from oracle import sparf_oracle as O
+    from sparf_b200.frequency_nerf import FrequencyEmbedder, NeRF
+    opt = common.make_opt(barf_c2f=c2f)
+    nerf = NeRF(opt).cuda()
+    nerf.progress.data.fill_(0.3)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = ((torch.rand(5, 37, 3, device="cuda", generator=g) - 0.5) * 4).requires_grad_(True)
+    L = 10
+    enc = nerf.positional_encoding(opt, x, FrequencyEmbedder(opt), L)
+    mask = O.c2f_weights(L, 0.3, c2f, device="cuda", dtype=torch.float64)
+    x64 = x.detach().double().requires_grad_(True)
+    ref = O.posenc(x64, L, mask)
+    assert enc.shape == ref.shape == (5, 37, 6 * L)
+    # the argument of the top band is ~3e3 rad: one fp32 ulp of the product is 2.4e-4 rad
+    assert (enc.double() - ref).abs().max().item() < 5e-4
+    w = torch.randn(enc.shape, device="cuda", generator=g)
+    (enc * w).sum().backward()
+    (ref * w.double()).sum().backward()
+    assert rel_err(x.grad, x64.grad) < 2e-3
+    plain = FrequencyEmbedder(opt)(opt, x.detach(), 4)
+    assert (plain.double() - O.posenc(x.detach().double(), 4, None)).abs().max().item() < 1e-5
