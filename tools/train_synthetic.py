@@ -91,7 +91,7 @@ def main(argv=None):
     step = GraphedStep(iteration, (), warmup=2)
     losses = []
     for it in range(args.steps):
-        losses.append(step())
+        losses.append(step().clone())     # (the graph's output tensor is static: keep a copy of its value)
         if not args.quiet and (it % 50 == 0 or it == args.steps - 1):
             print("iter %4d  photometric loss %.5f" % (it, float(losses[-1])))
     torch.cuda.synchronize()
