@@ -10,11 +10,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fine", [0, 1])
-def test_training_loop_converges(fine):
+@pytest.mark.parametrize("fine,poses", [(0, 0), (1, 0), (0, 1)])
+def test_training_loop_converges(fine, poses):
+    """coarse only / hierarchical / joint pose-NeRF (BARF mask advancing on the device, second fused-Adam group for the
+    9-D pose embeddings)"""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import train_synthetic
-    first, last = train_synthetic.main(["--steps", "300", "--quiet", "--fine", str(fine), "--rays", "768"])
-    print("fine=%d: loss %.5f -> %.5f" % (fine, first, last))
+    res = train_synthetic.main(["--steps", "300", "--quiet", "--fine", str(fine), "--poses", str(poses), "--rays", "768"])
+    first, last = res[0], res[1]
+    print("fine=%d poses=%d: loss %.5f -> %.5f" % (fine, poses, first, last))
     assert last == last and first == first            # finite
     assert last < 0.6 * first, (first, last)

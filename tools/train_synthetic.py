@@ -30,6 +30,9 @@ def main(argv=None):
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--fine", type=int, default=0)
     ap.add_argument("--lr", type=float, default=1e-3)
+    ap.add_argument("--poses", type=int, default=0, help="1: joint pose-NeRF training from perturbed poses (BARF c2f mask)")
+    ap.add_argument("--pose-noise", type=float, default=0.03)
+    ap.add_argument("--lr-pose", type=float, default=2e-3)
     ap.add_argument("--quiet", action="store_true")
     args = ap.parse_args(argv)
 
@@ -42,7 +45,7 @@ def main(argv=None):
     dev = torch.device("cuda")
     B, (H, W) = args.views, args.size
     opt = common.make_opt(S=args.samples, S_fine=args.samples, fine=bool(args.fine), rand_rays=args.rays, stratified=True,
-                          depth_range=(1.2, 5.2))
+                          depth_range=(1.2, 5.2), barf_c2f=(0.1, 0.5) if args.poses else None)
     opt.sample_fraction_in_fg_mask = 0.0
     opt.sampled_fraction_in_center = 0.0
     data = common.make_scene(0, B, H, W)
@@ -52,9 +55,9 @@ def main(argv=None):
 
     # ---- teacher: fixed "peaky" weights, renders the ground-truth views (val mode: deterministic, full image)
     teacher = Graph(opt, dev)
-    teacher.nerf.load_state_dict(common.det_weights(opt, 5, peaky=True, sigma_bias=-2.0))
+    teacher.nerf.load_state_dict(common.det_weights(opt, 5, peaky=True, sigma_bias=-2.0, progress=1.0))
     if args.fine:
-        teacher.nerf_fine.load_state_dict(common.det_weights(opt, 82, peaky=True, sigma_bias=-2.0))
+        teacher.nerf_fine.load_state_dict(common.det_weights(opt, 82, peaky=True, sigma_bias=-2.0, progress=1.0))
     teacher.eval()
     with torch.no_grad():
         full = teacher.forward(opt, data, iter=10 ** 9, mode="val")
@@ -63,9 +66,32 @@ def main(argv=None):
 
     # ---- student + the reference-shaped training objects
     torch.manual_seed(0)
-    net = Graph(opt, dev)
+    pose_net = None
+    if args.poses:      # joint pose-NeRF training (joint_pose_nerf_trainer.py): perturbed initial poses, 9-D embedding
+        from sparf_b200.poses_models import FirstTwoColunmnsPoseParameters
+        init = common.perturb_poses(data.pose.cpu(), 0, sigma=args.pose_noise).to(dev)
+        pose_net = FirstTwoColunmnsPoseParameters(opt, nbr_poses=B, initial_poses_w2c=init, device=dev).to(dev)
+
+        class PoseGraph(Graph):
+            def get_w2c_pose(self, opt, data_dict, mode=None):
+                return pose_net.get_w2c_poses()
+
+        net = PoseGraph(opt, dev)
+    else:
+        net = Graph(opt, dev)
     net.train()
     net.device_side_rng = True
+
+    def pose_error():
+        """mean rotation angle (deg) and camera-centre distance between the current estimates and the true poses, WITHOUT
+        the similarity alignment the reference's evaluation applies first (a jointly optimised scene is only defined up to
+        a global similarity, so this number need not shrink; it is printed for orientation only)"""
+        est, gt = pose_net.get_w2c_poses().detach(), data.pose
+        R = est[:, :, :3] @ gt[:, :, :3].transpose(1, 2)
+        ang = torch.acos(((R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2] - 1) / 2).clamp(-1, 1)) * 180 / 3.14159265
+        c_est = -(est[:, :, :3].transpose(1, 2) @ est[:, :, 3:])[..., 0]
+        c_gt = -(gt[:, :, :3].transpose(1, 2) @ gt[:, :, 3:])[..., 0]
+        return ang.mean().item(), (c_est - c_gt).norm(dim=-1).mean().item()
 
     class TrainData:
         all = data
@@ -78,15 +104,28 @@ def main(argv=None):
     sampler = RaySamplingStrategy(opt, data_dict=data, device=dev)
     flat = FlatParameters(net.get_network_components())
     adam = FusedAdam(flat, lr=args.lr, gamma=(1e-4 / args.lr) ** (1.0 / max(args.steps, 1)), max_norm=0.1)
+    flat_pose = adam_pose = None
+    if pose_net is not None:      # second optimiser group: poses, unclipped (default_config.py:43), own learning rate
+        flat_pose = FlatParameters([pose_net])
+        adam_pose = FusedAdam(flat_pose, lr=args.lr_pose, gamma=(1e-5 / args.lr_pose) ** (1.0 / max(args.steps, 1)))
+    progress_step = torch.full((), 1.0 / max(args.steps, 1), device=dev)
 
     def iteration():
         flat.zero_grad()
+        if flat_pose is not None:
+            flat_pose.zero_grad()
+            for m in net.get_network_components():           # BARF schedule: progress = iteration / max_iter, on the device
+                m.progress.data.add_(progress_step).clamp_(max=1.0)
         rays = sampler(opt.nerf.rand_rays)                       # device-side torch.randperm: fresh rays every replay
         out = net.render_image_at_specific_rays(opt, data, iter=0, ray_idx=rays, mode="train")
         loss = loss_module.compute_loss(opt, data, out, iteration=0, mode="train")[0]["all"]
         loss.backward()
         adam.step()
+        if adam_pose is not None:
+            adam_pose.step()
         return loss.detach()
+
+    err0 = pose_error() if pose_net is not None else None
 
     step = GraphedStep(iteration, (), warmup=2)
     losses = []
@@ -97,9 +136,15 @@ def main(argv=None):
     torch.cuda.synchronize()
     vals = torch.stack(losses).float().cpu()
     k = max(1, args.steps // 10)
+    if pose_net is not None:
+        err1 = pose_error()
+        if not args.quiet:
+            print("unaligned pose offset (rotation deg, camera centre): initial %.3f / %.4f -> final %.3f / %.4f" % (err0 + err1))
+        return vals[:k].mean().item(), vals[-k:].mean().item(), err0, err1
     return vals[:k].mean().item(), vals[-k:].mean().item()
 
 
 if __name__ == "__main__":
-    first, last = main()
+    res = main()
+    first, last = res[0], res[1]
     print("mean loss of the first 10%% of the iterations: %.5f   of the last 10%%: %.5f" % (first, last))
