@@ -58,7 +58,12 @@ enum {
   SPARF_ENGINE_SIMT_FP32 = 1, /* CUDA-core FFMA, fp32 throughout (bit-level twin of the reference) */
   SPARF_ENGINE_TC_3X = 2, /* tcgen05: x*W = x_hi*W_hi + x_lo*W_hi + x_hi*W_lo on 16-bit halves (fp16 in the
                              forward, bf16 for gradients), fp32 TMEM accumulation: the parity engine */
-  SPARF_ENGINE_TC_1X = 3  /* tcgen05, single 16-bit pass ("fast", NOT within the 1e-4 parity bound) */
+  SPARF_ENGINE_TC_1X = 3, /* tcgen05, single 16-bit pass ("fast", NOT within the 1e-4 parity bound) */
+  SPARF_ENGINE_TC_3X_W1 = 4 /* TC_3X forward and input / pose gradients (parity), but the wide layers' WEIGHT gradients
+                               dW = G^T X in ONE bf16 pass over the hi halves of the saved images (and their bias gradients
+                               as column sums of G_hi): the weight-gradient kernel reads half the bytes.  Non-default,
+                               reduced precision (8-bit factors; the rounding errors average over the batch):
+                               profiles/r02_engine_errors.md tabulates its error against fp64 */
 };
 
 typedef void* sparf_stream_t; /* cudaStream_t */

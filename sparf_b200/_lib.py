@@ -10,8 +10,8 @@ from . import build as _build
 
 MAX_TRUNK = 12
 
-ENGINE_AUTO, ENGINE_SIMT_FP32, ENGINE_TC_3X, ENGINE_TC_1X = 0, 1, 2, 3
-ENGINES = {"auto": 0, "simt_fp32": 1, "tc_3x": 2, "tc_1x": 3}
+ENGINE_AUTO, ENGINE_SIMT_FP32, ENGINE_TC_3X, ENGINE_TC_1X, ENGINE_TC_3X_W1 = 0, 1, 2, 3, 4
+ENGINES = {"auto": 0, "simt_fp32": 1, "tc_3x": 2, "tc_1x": 3, "tc_3x_w1": 4}
 
 
 class SparfMLP(ctypes.Structure):

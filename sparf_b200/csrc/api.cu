@@ -39,10 +39,13 @@ static bool device_is_sm100() {
 }
 
 // AUTO -> the tensor-core engine when this MLP shape is covered by it, else SIMT
+static bool is_tc(int engine) { return engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X || engine == SPARF_ENGINE_TC_3X_W1; }
+static bool is_tc3(int engine) { return engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_3X_W1; }   // engines that keep a tape
+
 static int resolve_engine(const SparfMLP* mlp, int engine) {
 #ifdef SPARF_WITH_TC
   if (engine == SPARF_ENGINE_AUTO) return tc_supports(mlp) && device_is_sm100() ? SPARF_ENGINE_TC_3X : SPARF_ENGINE_SIMT_FP32;
-  if ((engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X) && !tc_supports(mlp)) return -1;
+  if (is_tc(engine) && !tc_supports(mlp)) return -1;
 #else
   if (engine == SPARF_ENGINE_AUTO) return SPARF_ENGINE_SIMT_FP32;
 #endif
@@ -60,7 +63,7 @@ extern "C" uint64_t sparf_launch_count(void) { return g_launch_count; }
 extern "C" int sparf_engine_available(int engine) {
   if (engine == SPARF_ENGINE_SIMT_FP32) return 1;
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X) return device_is_sm100() ? 1 : 0;
+  if (is_tc(engine)) return device_is_sm100() ? 1 : 0;
 #endif
   return 0;
 }
@@ -69,7 +72,7 @@ extern "C" size_t sparf_mlp_workspace_bytes(const SparfMLP* mlp, int32_t R, int3
   if (!mlp || R <= 0 || S <= 0) return 0;
   engine = resolve_engine(mlp, engine);
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X) return tc_workspace_bytes(mlp, R, S, backward, engine);
+  if (is_tc(engine)) return tc_workspace_bytes(mlp, R, S, backward, engine);
 #endif
   return simt_workspace_bytes(mlp, R, S, backward);
 }
@@ -84,7 +87,7 @@ extern "C" int sparf_mlp_forward(const SparfMLP* mlp, int32_t engine, int32_t R,
   if (engine == SPARF_ENGINE_SIMT_FP32)
     return simt_mlp_forward(mlp, R, S, origins, dirs, t, noise, sigma, rgb, workspace, workspace_bytes, (cudaStream_t)stream);
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X)
+  if (is_tc(engine))
     return tc_mlp_forward(mlp, engine, R, S, origins, dirs, t, noise, sigma, rgb, workspace, workspace_bytes, (cudaStream_t)stream);
 #endif
   set_error("mlp_forward: engine %d not available in this build", engine);
@@ -102,7 +105,7 @@ extern "C" int sparf_mlp_backward(const SparfMLP* mlp, int32_t engine, int32_t R
   if (engine == SPARF_ENGINE_SIMT_FP32)
     return simt_mlp_backward(mlp, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace, workspace_bytes, (cudaStream_t)stream);
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3X || engine == SPARF_ENGINE_TC_1X)
+  if (is_tc(engine))
     return tc_mlp_backward(mlp, engine, R, S, origins, dirs, t, noise, d_sigma, d_rgb, grad, d_origins, d_dirs, workspace, workspace_bytes, (cudaStream_t)stream);
 #endif
   set_error("mlp_backward: engine %d not available in this build", engine);
@@ -115,7 +118,7 @@ extern "C" size_t sparf_mlp_tape_bytes(const SparfMLP* mlp, int32_t engine, int3
   if (!mlp || R <= 0 || S <= 0) return 0;
   engine = resolve_engine(mlp, engine);
 #ifdef SPARF_WITH_TC
-  if (engine == SPARF_ENGINE_TC_3X) return tc_tape_bytes(mlp, R, S);
+  if (is_tc3(engine)) return tc_tape_bytes(mlp, R, S);
 #endif
   return 0;
 }
@@ -126,7 +129,7 @@ extern "C" int sparf_mlp_forward_tape(const SparfMLP* mlp, int32_t engine, int32
                                       sparf_stream_t stream) {
   SPARF_REQUIRE(mlp && R > 0 && S > 0 && origins && dirs && t && sigma && rgb && tape, "mlp_forward_tape: bad arguments");
 #ifdef SPARF_WITH_TC
-  if (resolve_engine(mlp, engine) == SPARF_ENGINE_TC_3X)
+  if (is_tc3(resolve_engine(mlp, engine)))
     return tc_mlp_forward_tape(mlp, SPARF_ENGINE_TC_3X, R, S, origins, dirs, t, noise, sigma, rgb, tape, tape_bytes, workspace,
                                workspace_bytes, (cudaStream_t)stream);
 #endif
@@ -142,8 +145,8 @@ extern "C" int sparf_mlp_backward_tape(const SparfMLP* mlp, int32_t engine, int3
   SPARF_REQUIRE(mlp && R > 0 && S > 0 && origins && dirs && t && sigma && rgb && d_sigma && d_rgb && grad && tape,
                 "mlp_backward_tape: bad arguments");
 #ifdef SPARF_WITH_TC
-  if (resolve_engine(mlp, engine) == SPARF_ENGINE_TC_3X)
-    return tc_mlp_backward_tape(mlp, SPARF_ENGINE_TC_3X, R, S, origins, dirs, t, sigma, rgb, d_sigma, d_rgb, grad, d_origins,
+  if (is_tc3(resolve_engine(mlp, engine)))
+    return tc_mlp_backward_tape(mlp, resolve_engine(mlp, engine), R, S, origins, dirs, t, sigma, rgb, d_sigma, d_rgb, grad, d_origins,
                                 d_dirs, tape, tape_bytes, workspace, workspace_bytes, (cudaStream_t)stream);
 #endif
   set_error("mlp_backward_tape: only the tcgen05 engine keeps a tape");

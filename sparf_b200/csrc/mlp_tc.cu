@@ -1,4 +1,4 @@
-// tcgen05 engine for the NeRF MLP (SPARF_ENGINE_TC_3X / TC_1X), sm_100a.
+// tcgen05 engine for the NeRF MLP (SPARF_ENGINE_TC_3X / TC_1X / TC_3X_W1), sm_100a.
 //
 // CHAIN KERNELS (tc_mlp_fwd_kernel, tc_mlp_dgrad_kernel): persistent, warp-specialised, one CTA per SM.  A CTA owns
 // 128 sample rows at a time (one TMEM lane per row) and pushes them through all tensor-core layers without the
@@ -1421,6 +1421,8 @@ struct WgradJob {
   int ldw, col0;         // row stride and first column
   int enc_cols;          // 1: N' side is the encoder block (internal column order -> reference columns)
   float* colsum;         // optional: colsum[f] += sum_rows G[row][f]  (the layer's bias gradient), else NULL
+  int passes;            // 3: G_hi X_hi + G_lo X_hi + G_hi X_lo;  1 (SPARF_ENGINE_TC_3X_W1): G_hi X_hi, the lo halves are
+                         // not read at all (the bias gradients become column sums of G_hi)
 };
 constexpr int kMaxWgradJobs = 160;
 constexpr int kBwdSplitDefault = 1;     // sub-chunks of the backward pipeline (dgrad(k + 1) beside wgrad(k)); 1 = off
@@ -1458,7 +1460,10 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int nq = (job.tile_end - job.tile_begin) * 4;    // quarter tiles (32 rows) to stream
-  const uint32_t stage_tx = (uint32_t)(job.mblk + job.nblk) * 2u * 4096u;
+  const bool one_pass = job.passes == 1;
+  // one pass: both sides load their hi halves only (the bias gradients = column sums of G are then sums of G_hi too)
+  const int g_parts = one_pass ? 1 : 2, x_parts = g_parts;
+  const uint32_t stage_tx = (uint32_t)(job.mblk * g_parts + job.nblk * x_parts) * 4096u;
 
   if (warp == 0) {
     // producer warp (uniform control flow, an elected lane issues).  A second producer warp for the activation side
@@ -1472,10 +1477,12 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
         // stage layout: [G hi: mblk x 4 KB][G lo][X hi: nblk x 4 KB][X lo], 4 KB = rows [32 qr, 32 qr + 32) of a block
         mbar_arrive_expect_tx(&full[stage], stage_tx);
         for (int part = 0; part < 2; ++part) {
-          for (int b = 0; b < job.mblk; ++b)
-            bulk_g2s(st + (part * 4 + b) * 4096, img.at(job.t_g, tile, b, part) + qr * 4096, 4096, &full[stage]);
-          for (int b = 0; b < job.nblk; ++b)
-            bulk_g2s(st + (8 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
+          if (part < g_parts)
+            for (int b = 0; b < job.mblk; ++b)
+              bulk_g2s(st + (part * 4 + b) * 4096, img.at(job.t_g, tile, b, part) + qr * 4096, 4096, &full[stage]);
+          if (part < x_parts)
+            for (int b = 0; b < job.nblk; ++b)
+              bulk_g2s(st + (8 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
         }
       }
       __syncwarp();
@@ -1498,8 +1505,10 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
             const uint64_t x_hi = make_smem_desc_mn(st + 8 * 4096 + ks * 2048, 4096);
             const uint64_t x_lo = make_smem_desc_mn(st + 12 * 4096 + ks * 2048, 4096);
             umma_ss(d_addr, g_hi, x_hi, idesc, (qi | ks) != 0);
-            umma_ss(d_addr, g_lo, x_hi, idesc, 1u);
-            umma_ss(d_addr, g_hi, x_lo, idesc, 1u);
+            if (!one_pass) {
+              umma_ss(d_addr, g_lo, x_hi, idesc, 1u);
+              umma_ss(d_addr, g_hi, x_lo, idesc, 1u);
+            }
           }
         }
         umma_commit(&empty[stage]);
@@ -1532,7 +1541,8 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
           for (int i = 0; i < 8; ++i) {
             const uint32_t off = (uint32_t)(rg * 8 + i) * 128u + (uint32_t)((c ^ i) << 4);
             float x[8];
-            unpack8(*reinterpret_cast<const uint4*>(bh + off), *reinterpret_cast<const uint4*>(bl + off), x);
+            unpack8(*reinterpret_cast<const uint4*>(bh + off),
+                    one_pass ? make_uint4(0u, 0u, 0u, 0u) : *reinterpret_cast<const uint4*>(bl + off), x);
 #pragma unroll
             for (int k = 0; k < 8; ++k) cs[k] += x[k];
           }
@@ -2368,6 +2378,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     while (nsplit > 1 && ntiles / nsplit < num_sms()) --nsplit;
     const int nd_sms = std::max(16, std::min(num_sms() - 16, bwd_split_env("SPARF_TC_BWD_ND", kBwdNdDefault)));
 
+    const int wg_passes = engine == SPARF_ENGINE_TC_3X_W1 ? 1 : 3;
     // 3. (helper) weight-gradient job table = (layer, slab of row tiles) over tiles [t_lo, t_hi), ~`ctas` CTAs, one per SM
     auto wgrad_launch = [&](int t_lo, int t_hi, int ctas, cudaStream_t ws) -> int {
       WgradJobs jobs_tab;
@@ -2382,6 +2393,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
           j.tile_begin = t_lo + (int)((long long)nt * sl / slabs);
           j.tile_end = t_lo + (int)((long long)nt * (sl + 1) / slabs);
           j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum;
+          j.passes = wg_passes;
           jobs[nj++] = j;
         }
       };
