@@ -2,7 +2,7 @@
 """Benchmark of the SPARF ray-marching hot path (BASELINE.json metric: rays/s, fwd+bwd, 128 samples/ray).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c2h|c3|c4|c5] [--impl ours|reference]
-                    [--engine auto|simt_fp32|tc_3x] [--graph 0|1] [--device cpu|cuda (reference arm)]
+                    [--engine auto|simt_fp32|tc_3x|tc_3x_w1 (reduced precision, labelled so)] [--graph 0|1] [--device cpu|cuda (reference arm)]
 
 One "step" = one pass of the hot path over one synthetic ray batch of a BASELINE config, through the public API
 (`Graph.render_image_at_specific_rays` + the loss module's `compute_loss` + `backward()`), gradients zeroed each step:
@@ -72,6 +72,10 @@ CONFIGS = {
 METRIC = "rays/sec (fwd+bwd, 128 samples/ray)"
 DTYPE = ("fp32 in / out; GEMMs on tcgen05 kind::f16 with a 3-pass error-compensated split (fp16 halves forward, bf16 "
          "halves backward), fp32 TMEM accumulation; fp32 CUDA cores for encoding / activations / compositing")
+ENGINE_DTYPE = {"auto": DTYPE, "tc_3x": DTYPE,
+                "tc_3x_w1": "REDUCED PRECISION (non-default engine, not a parity number): as tc_3x, but the weight gradients in "
+                            "ONE bf16 pass over the hi halves of the saved images",
+                "tc_1x": "REDUCED PRECISION (non-default engine, not a parity number): single 16-bit pass forward"}
 
 
 def load_peaks():
@@ -425,7 +429,7 @@ def run_ours(args):
         cpu = cpu_baseline(args.config, budget_s=25.0)
     line = dict(metric=METRIC, value=value, unit="rays/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling=cfg["scaling"], vs_baseline=None,
-                dtype=DTYPE if args.engine in ("auto", "tc_3x") else "fp32 (CUDA cores)", data="synthetic",
+                dtype=ENGINE_DTYPE.get(args.engine, "fp32 (CUDA cores)"), data="synthetic",
                 config=dict(workload=cfg["desc"], name=args.config, rays_per_gpu=rays_local, global_rays=rays_per_step,
                             samples_per_ray=cfg["S"], fine_samples_per_ray=(cfg["S"] + cfg["S_fine"]) if cfg["fine"] else 0,
                             l2_flush_between_steps=True,
