@@ -130,7 +130,7 @@ extern "C" int sparf_mlp_forward_tape(const SparfMLP* mlp, int32_t engine, int32
   SPARF_REQUIRE(mlp && R > 0 && S > 0 && origins && dirs && t && sigma && rgb && tape, "mlp_forward_tape: bad arguments");
 #ifdef SPARF_WITH_TC
   if (is_tc3(resolve_engine(mlp, engine)))
-    return tc_mlp_forward_tape(mlp, SPARF_ENGINE_TC_3X, R, S, origins, dirs, t, noise, sigma, rgb, tape, tape_bytes, workspace,
+    return tc_mlp_forward_tape(mlp, resolve_engine(mlp, engine), R, S, origins, dirs, t, noise, sigma, rgb, tape, tape_bytes, workspace,
                                workspace_bytes, (cudaStream_t)stream);
 #endif
   set_error("mlp_forward_tape: only the tcgen05 engine keeps a tape (sparf_mlp_tape_bytes returned 0)");

@@ -132,7 +132,7 @@ struct FwdParams {
   int num_tiles;
   int passes;              // 3 (compensated) or 1
   int ncopies;             // replicas of the packed weight stream
-  int save;                // dump A-operand images
+  int save;                // dump A-operand images: 0 no, 1 (hi, lo) halves, 2 hi halves only (SPARF_ENGINE_TC_3X_W1)
   Images img;
 };
 
@@ -148,6 +148,7 @@ struct BwdParams {
   const float* w9;         // [3,128]
   long long M;
   int num_tiles;
+  int hi_only;             // 1 (SPARF_ENGINE_TC_3X_W1): gradient images read by the weight-gradient kernel only keep their hi half
   Images img;
 };
 
@@ -306,14 +307,22 @@ __device__ __forceinline__ void st_global_256(uint8_t* p, uint32_t a0, uint32_t 
                ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3)
                : "memory");
 }
-__device__ __forceinline__ void store16_image(const Split16& v, int row, int col0, uint8_t* g_hi, uint8_t* g_lo) {
+// bf16 hi words only (= the hi words of split16<false>): the single-pass weight-gradient engine's tape
+__device__ __forceinline__ void hi16_bf16(const float (&f)[16], uint32_t (&hi)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    hi[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+__device__ __forceinline__ void store16_image(const Split16& v, int row, int col0, uint8_t* g_hi, uint8_t* g_lo, bool with_lo = true) {
   const uint32_t off = sw128_offset(row, col0) & ~31u;
   if (row & 1) {   // odd rows: the swizzle swaps the two chunks of the sector
     st_global_256(g_hi + off, v.hi[4], v.hi[5], v.hi[6], v.hi[7], v.hi[0], v.hi[1], v.hi[2], v.hi[3]);
-    st_global_256(g_lo + off, v.lo[4], v.lo[5], v.lo[6], v.lo[7], v.lo[0], v.lo[1], v.lo[2], v.lo[3]);
+    if (with_lo) st_global_256(g_lo + off, v.lo[4], v.lo[5], v.lo[6], v.lo[7], v.lo[0], v.lo[1], v.lo[2], v.lo[3]);
   } else {
     st_global_256(g_hi + off, v.hi[0], v.hi[1], v.hi[2], v.hi[3], v.hi[4], v.hi[5], v.hi[6], v.hi[7]);
-    st_global_256(g_lo + off, v.lo[0], v.lo[1], v.lo[2], v.lo[3], v.lo[4], v.lo[5], v.lo[6], v.lo[7]);
+    if (with_lo) st_global_256(g_lo + off, v.lo[0], v.lo[1], v.lo[2], v.lo[3], v.lo[4], v.lo[5], v.lo[6], v.lo[7]);
   }
 }
 __device__ __forceinline__ void store16_part(const uint32_t (&w)[8], int row, int col0, uint8_t* blk) {
@@ -687,7 +696,8 @@ constexpr int kOffRingTInf = 2 * kChunkBytes, kStagesTInf = 10;
 static_assert(kOffRingTSave + kStagesTSave * kChunkBytes <= kOffBias && kOffRingTInf + kStagesTInf * kChunkBytes <= kOffBias,
               "tensor-memory-operand forward: shared-memory map");
 
-template <bool kF16, bool kTmemA = false>
+// kHiTape (with kTmemA, p.save == 2): the tape images get their bf16 hi halves only (SPARF_ENGINE_TC_3X_W1)
+template <bool kF16, bool kTmemA = false, bool kHiTape = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -810,13 +820,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
     const uint32_t store_id = (uint32_t)(2 + kEpiWarps + kIssuers - 1 - warp);   // warp 19 -> 0, warp 18 -> 1
     if (p.save) {
       uint8_t* stg = smem + kOffStgT;
+      constexpr int nparts = kHiTape ? 1 : 2;
       Trace tr; trace_begin(tr);
       for (int it = 0; it < my_tiles; ++it) {
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         for (int l = 0; l < 8; ++l) {
           const int t_img = l == 7 ? T_FEAT : T_H0 + l;
-          for (int jp = 0; jp < 8; ++jp) {                         // (block j, part)
-            const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + (uint32_t)jp;
+          for (int jq = 0; jq < 4 * nparts; ++jq) {                // (block j, part)
+            const int jp = nparts == 2 ? jq : 2 * jq;
+            const uint32_t qs = (uint32_t)nparts * (32u * (uint32_t)it + 4u * (uint32_t)l) + (uint32_t)jq;
             if (qs % (uint32_t)kStoreWarps != store_id) continue;
             const uint32_t slot = qs % (uint32_t)kFwdSlots, k = qs / (uint32_t)kFwdSlots;
             twait(tr, 0, &cs.g_ready[slot], k & 1);
@@ -860,6 +872,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
       const bool valid = m < p.M;
       const long long ray = valid ? m / p.S : 0;
       const bool save = p.save != 0;
+      constexpr int nparts = kHiTape ? 1 : 2;      // halves of the tape images that are written
 
       // ---------------- positional encoding -> A_enc (internal column order: x y z 0 | (sin,cos) pairs)
       {
@@ -894,6 +907,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
         if (lane == 0) mbar_arrive(&cs.a_ready[4]);
         if (save) {
           if (kF16) split16<false>(vals, sp);
+          // (both halves whatever the tape mode: the ray-gradient kernel rebuilds sin / cos from this image)
           store16_image(sp, row, cq * kEpiCols, p.img.at(T_ENC, tile, 0, 0), p.img.at(T_ENC, tile, 0, 1));
         }
         trace_toc(tr, 3, tenc);
@@ -962,11 +976,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
                 for (int i = 0; i < 16; ++i) m16 |= (f[i] > 0.f ? 1u : 0u) << i;
                 mbits[j >> 1] |= m16 << (16 * (j & 1));
                 Split16 sp;
-                split16<false>(f, sp);
+                if (nparts == 2) split16<false>(f, sp); else hi16_bf16(f, sp.hi);
                 uint8_t* stg = smem + kOffStgT;
 #pragma unroll
                 for (int part = 0; part < 2; ++part) {
-                  const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + 2u * (uint32_t)j + (uint32_t)part;
+                  if (part >= nparts) break;
+                  const uint32_t qs = (uint32_t)nparts * (32u * (uint32_t)it + 4u * (uint32_t)l + (uint32_t)j) + (uint32_t)part;
                   const uint32_t slot = qs % (uint32_t)kFwdSlots, k = qs / (uint32_t)kFwdSlots;
                   if (k > 0) twait(tr, 1, &cs.s_free[slot], (k - 1) & 1);
                   store16_part(part == 0 ? sp.hi : sp.lo, row, cq * kEpiCols, stg + (size_t)slot * kChunkBytes);
@@ -1028,7 +1043,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
             }
             if (save) {   // hid image for the 128->3 head's weight gradient and its ReLU mask
               split16<false>(f, sp);
-              store16_image(sp, row, cq * kEpiCols, p.img.at(T_HID, tile, j, 0), p.img.at(T_HID, tile, j, 1));
+              store16_image(sp, row, cq * kEpiCols, p.img.at(T_HID, tile, j, 0), p.img.at(T_HID, tile, j, 1), nparts == 2);
             }
           } else if (kTmemA) {
             split16<kF16>(f, sp);
@@ -1043,7 +1058,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
               uint8_t* stg = smem + kOffStgT;
 #pragma unroll
               for (int part = 0; part < 2; ++part) {
-                const uint32_t qs = 64u * (uint32_t)it + 8u * (uint32_t)l + 2u * (uint32_t)j + (uint32_t)part;
+                if (part >= nparts) break;
+                const uint32_t qs = (uint32_t)nparts * (32u * (uint32_t)it + 4u * (uint32_t)l + (uint32_t)j) + (uint32_t)part;
                 const uint32_t slot = qs % (uint32_t)kFwdSlots, k = qs / (uint32_t)kFwdSlots;
                 if (k > 0) twait(tr, 1, &cs.s_free[slot], (k - 1) & 1);
                 store16_part(part == 0 ? sp.hi : sp.lo, row, cq * kEpiCols, stg + (size_t)slot * kChunkBytes);
@@ -1061,7 +1077,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_fwd_kernel(const FwdParams
             if (save) {
               const int tsave = l == 7 ? T_FEAT : T_H0 + l;
               if (kF16) split16<false>(f, sp);
-              store16_image(sp, row, cq * kEpiCols, p.img.at(tsave, tile, j, 0), p.img.at(tsave, tile, j, 1));
+              store16_image(sp, row, cq * kEpiCols, p.img.at(tsave, tile, j, 0), p.img.at(tsave, tile, j, 1), nparts == 2);
             }
           }
         }
@@ -1209,7 +1225,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_dgrad_kernel(const BwdPara
             if (kTmemA) {
               // (hi | lo) of a block are adjacent in the slot AND in the HBM image: one 32 KB bulk store.  A dummy tile
               // (never with stand-alone CTAs) would still need its (empty) group for the in-flight accounting.
-              if (tile_ok) bulk_s2g(p.img.at(t_out, tile, j, 0), src_hi, 2 * kChunkBytes);
+              // hi_only (SPARF_ENGINE_TC_3X_W1): images only the single-pass weight-gradient kernel reads keep their hi half
+              const bool both = !p.hi_only || t_out == T_GHID || step == kNumBwdLayers || t_out == t_g(4);
+              if (tile_ok) bulk_s2g(p.img.at(t_out, tile, j, 0), src_hi, (both ? 2 : 1) * kChunkBytes);
               bulk_commit_group();
               bulk_wait_read<kStoreInflight - 1>();
               if (q + 1u >= (uint32_t)kStoreInflight)
@@ -1428,7 +1446,8 @@ constexpr int kMaxWgradJobs = 160;
 constexpr int kBwdSplitDefault = 1;     // sub-chunks of the backward pipeline (dgrad(k + 1) beside wgrad(k)); 1 = off
 constexpr int kBwdNdDefault = 88;       // SMs of the dgrad chain while a weight-gradient kernel runs beside it
 struct WgradJobs { WgradJob j[kMaxWgradJobs]; };   // passed by value (kernel parameter): no host->device copy per step
-constexpr int kWgStages = 3;
+constexpr int kWgStages = 3;                // three passes: 3 stages of 64 KB; one pass (hi halves only): 6 stages of 32 KB, so
+constexpr int kWgMaxStages = 6;             // that the same number of bytes is in flight per SM (the kernel is HBM-latency bound)
 constexpr int kWgStageBytes = 16 * 4096;   // (4 G blocks + 4 X blocks) x (hi, lo) x 32 rows x 128 B
 constexpr int kWgSmem = kWgStages * kWgStageBytes + 256;
 
@@ -1437,17 +1456,24 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kWgStages;
-  uint64_t* done = bars + 2 * kWgStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  uint64_t* empty = bars + kWgMaxStages;
+  uint64_t* done = bars + 2 * kWgMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgMaxStages + 1);
   const WgradJob& job = jobs.j[blockIdx.x];
+  const bool one_pass = job.passes == 1;
+  // one pass: both sides load their hi halves only (the bias gradients = column sums of G are then sums of G_hi too);
+  // stage = [G hi: 4 x 4 KB][X hi: 4 x 4 KB], twice as many stages
+  const int g_parts = one_pass ? 1 : 2, x_parts = g_parts;
+  const uint32_t nstages = one_pass ? 2u * kWgStages : (uint32_t)kWgStages;
+  const uint32_t stage_bytes = one_pass ? (uint32_t)kWgStageBytes / 2u : (uint32_t)kWgStageBytes;
+  const uint32_t x_blk0 = one_pass ? 4u : 8u;      // first 4 KB block of the X side within a stage
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ncols = job.nblk * 64;                       // N'
   const int mhalves = job.mblk / 2;                      // accumulators of 128 rows
   const uint32_t tmem_cols = (mhalves * ncols <= 64) ? 64 : (mhalves * ncols <= 128 ? 128 : (mhalves * ncols <= 256 ? 256 : 512));
 
   if (tid == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 5); }   // MMA commit + 4 reducer warps
+    for (int i = 0; i < kWgMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 5); }   // MMA commit + 4 reducer warps
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -1460,9 +1486,6 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int nq = (job.tile_end - job.tile_begin) * 4;    // quarter tiles (32 rows) to stream
-  const bool one_pass = job.passes == 1;
-  // one pass: both sides load their hi halves only (the bias gradients = column sums of G are then sums of G_hi too)
-  const int g_parts = one_pass ? 1 : 2, x_parts = g_parts;
   const uint32_t stage_tx = (uint32_t)(job.mblk * g_parts + job.nblk * x_parts) * 4096u;
 
   if (warp == 0) {
@@ -1473,7 +1496,7 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
       const int tile = job.tile_begin + (qi >> 2), qr = qi & 3;
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
-        uint8_t* st = smem + stage * kWgStageBytes;
+        uint8_t* st = smem + stage * stage_bytes;
         // stage layout: [G hi: mblk x 4 KB][G lo][X hi: nblk x 4 KB][X lo], 4 KB = rows [32 qr, 32 qr + 32) of a block
         mbar_arrive_expect_tx(&full[stage], stage_tx);
         for (int part = 0; part < 2; ++part) {
@@ -1482,11 +1505,11 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
               bulk_g2s(st + (part * 4 + b) * 4096, img.at(job.t_g, tile, b, part) + qr * 4096, 4096, &full[stage]);
           if (part < x_parts)
             for (int b = 0; b < job.nblk; ++b)
-              bulk_g2s(st + (8 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
+              bulk_g2s(st + (x_blk0 + part * 4 + b) * 4096, img.at(job.t_x, tile, b, part) + qr * 4096, 4096, &full[stage]);
         }
       }
       __syncwarp();
-      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      if (++stage == nstages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc(128, ncols, 1, 1, 1);
@@ -1494,7 +1517,7 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
     for (int qi = 0; qi < nq; ++qi) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
-      const uint32_t st = smem_u32(smem + stage * kWgStageBytes);
+      const uint32_t st = smem_u32(smem + stage * stage_bytes);
       if (elect_one()) {
         for (int mh = 0; mh < mhalves; ++mh) {
           const uint32_t d_addr = tmem_base + (uint32_t)(mh * ncols);
@@ -1502,7 +1525,7 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
           for (int ks = 0; ks < 2; ++ks) {   // 32 rows = 2 x K16
             const uint64_t g_hi = make_smem_desc_mn(st + (0 + mh * 2) * 4096 + ks * 2048, 4096);
             const uint64_t g_lo = make_smem_desc_mn(st + (4 + mh * 2) * 4096 + ks * 2048, 4096);
-            const uint64_t x_hi = make_smem_desc_mn(st + 8 * 4096 + ks * 2048, 4096);
+            const uint64_t x_hi = make_smem_desc_mn(st + x_blk0 * 4096 + ks * 2048, 4096);
             const uint64_t x_lo = make_smem_desc_mn(st + 12 * 4096 + ks * 2048, 4096);
             umma_ss(d_addr, g_hi, x_hi, idesc, (qi | ks) != 0);
             if (!one_pass) {
@@ -1514,7 +1537,7 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
         umma_commit(&empty[stage]);
       }
       __syncwarp();
-      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      if (++stage == nstages) { stage = 0; phase ^= 1; }
     }
     if (elect_one()) umma_commit(done);
     __syncwarp();
@@ -1535,7 +1558,7 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
       for (int qi = 0; qi < nq; ++qi) {
         mbar_wait(&full[stage], phase);
         if (has) {
-          const uint8_t* bh = smem + stage * kWgStageBytes + blk * 4096;
+          const uint8_t* bh = smem + stage * stage_bytes + blk * 4096;
           const uint8_t* bl = bh + 4 * 4096;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -1549,7 +1572,7 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
       if (has) {
 #pragma unroll
@@ -1612,6 +1635,7 @@ struct ReduceJob {
   float* out;
   int ldo;
   float* out_bias;
+  int parts;           // 2: image = hi + lo halves; 1: hi half only (the lo half was not written: SPARF_ENGINE_TC_3X_W1)
 };
 
 struct ReduceJobs { ReduceJob j[16]; };
@@ -1646,7 +1670,7 @@ __global__ void __launch_bounds__(256) image_reduce_kernel(const __grid_constant
         const uint32_t off = sw128_offset(row, c * 8);
         const bool ok = m < M;
         vh[u] = ok ? __ldg(reinterpret_cast<const uint4*>(bh + off)) : make_uint4(0, 0, 0, 0);
-        vl[u] = ok ? __ldg(reinterpret_cast<const uint4*>(bl + off)) : make_uint4(0, 0, 0, 0);
+        vl[u] = (ok && job.parts == 2) ? __ldg(reinterpret_cast<const uint4*>(bl + off)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int k = 0; k < 3; ++k) gv[u][k] = (ok && k < nc) ? __ldg(job.g + m * job.gs + k) : 0.f;
       }
@@ -2086,7 +2110,7 @@ static void trace_dump(const char* what) {
 
 static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int S, const float* origins, const float* dirs,
                           const float* t, const float* noise, float* sigma, float* rgb, const uint8_t* packed,
-                          const float* raybias, const Images* img, cudaStream_t st, int ncopies = 1) {
+                          const float* raybias, const Images* img, cudaStream_t st, int ncopies = 1, int save_mode = 1) {
   FwdParams p;
   p.packed = packed;
   p.raybias = raybias;
@@ -2102,7 +2126,7 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
   p.num_tiles = (int)((p.M + kTileM - 1) / kTileM);
   p.passes = passes;
   p.ncopies = ncopies;
-  p.save = img != nullptr;
+  p.save = img != nullptr ? save_mode : 0;
   if (img) p.img = *img; else { for (int i = 0; i < T_COUNT; ++i) p.img.ptr[i] = nullptr; }
   static bool attr_set_dev[64] = {};
   int dev_ord = 0;
@@ -2111,6 +2135,7 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
   if (!attr_set) {
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
+    SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
     SPARF_CHECK_CUDA(cudaFuncSetAttribute(tc_mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes + 1024));
@@ -2119,7 +2144,11 @@ static int launch_forward(const SparfMLP* mlp, bool f16, int passes, int nr, int
     attr_set = true;
   }
   const int variant = fwd_variant(f16, passes, p.save != 0, p.num_tiles);
-  if (variant == FWD_TMEM) {
+  if (variant != FWD_TMEM && p.save == 2) p.save = 1;     // the shared-memory-operand kernels always write both halves
+  if (variant == FWD_TMEM && p.save == 2) {
+    tc_mlp_fwd_kernel<true, true, true><<<std::min(p.num_tiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(p);
+    TRACE_DUMP("forward (hi-only tape, A in TMEM)");
+  } else if (variant == FWD_TMEM) {
     tc_mlp_fwd_kernel<true, true><<<std::min(p.num_tiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(p);
     TRACE_DUMP(p.save ? "forward (tape, A in TMEM)" : "forward f16 (A in TMEM)");
   } else {
@@ -2257,7 +2286,9 @@ int tc_mlp_forward_tape(const SparfMLP* mlp, int engine, int R, int S, const flo
   }
   Images img;
   images_assign(img, ntiles, tp, nullptr);
-  rc = launch_forward(mlp, true, 3, R, S, origins, dirs, t, noise, sigma, rgb, packed, raybias, &img, st);
+  // TC_3X_W1: the weight gradients will take the hi halves only, so only those are written (the tape keeps its layout)
+  rc = launch_forward(mlp, true, 3, R, S, origins, dirs, t, noise, sigma, rgb, packed, raybias, &img, st, 1,
+                      engine == SPARF_ENGINE_TC_3X_W1 ? 2 : 1);
   // join: whatever follows on the caller's stream (the backward, or a reuse of the tape's memory) is ordered after the
   // side-stream packing, which has long finished by the time the forward kernel ends
   if (side && rc == SPARF_OK) SPARF_CHECK_CUDA(cudaStreamWaitEvent(st, side->packed, 0));
@@ -2364,7 +2395,9 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     }
 
     // 2. input-gradient chain
+    const int wg_passes = engine == SPARF_ENGINE_TC_3X_W1 ? 1 : 3;
     BwdParams bp;
+    bp.hi_only = wg_passes == 1;
     bp.packed = c.packed_b;
     bp.d_sigma = d_sigma + m0; bp.d_rgb = d_rgb + m0 * 3;
     bp.sigma = c.sigma; bp.rgb = c.rgb;
@@ -2378,7 +2411,6 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     while (nsplit > 1 && ntiles / nsplit < num_sms()) --nsplit;
     const int nd_sms = std::max(16, std::min(num_sms() - 16, bwd_split_env("SPARF_TC_BWD_ND", kBwdNdDefault)));
 
-    const int wg_passes = engine == SPARF_ENGINE_TC_3X_W1 ? 1 : 3;
     // 3. (helper) weight-gradient job table = (layer, slab of row tiles) over tiles [t_lo, t_hi), ~`ctas` CTAs, one per SM
     auto wgrad_launch = [&](int t_lo, int t_hi, int ctas, cudaStream_t ws) -> int {
       WgradJobs jobs_tab;
@@ -2459,6 +2491,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     int nrj = 0;
     auto add_red = [&](int t, int nblk, int nc, const float* g, int gs, float* out, int ldo, float* ob) {
       ReduceJob j; j.t = t; j.nblk = nblk; j.nc = nc; j.g = g; j.gs = gs; j.out = out; j.ldo = ldo; j.out_bias = ob;
+      j.parts = (tape && wg_passes == 1) ? 1 : 2;     // forward images of a TC_3X_W1 tape hold their hi halves only
       rj[nrj++] = j;
     };
     // (bias gradients = column sums of the gradient images are produced inside the weight-gradient kernel)

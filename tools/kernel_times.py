@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel device time of one MLP training step / inference forward (torch.profiler = CUPTI activity records, no
-replay, warm caches).  Usage: python tools/kernel_times.py [R S]"""
+replay, warm caches).  Usage: [SPARF_KT_ENGINE=tc_3x|tc_3x_w1] python tools/kernel_times.py [R S]"""
 import os
 import sys
 from collections import defaultdict
@@ -26,17 +26,18 @@ def main():
     d = torch.nn.functional.normalize(torch.randn(R, 3, device="cuda"), dim=-1).requires_grad_(True)
     t = torch.sort(torch.rand(R, S, device="cuda") * 4 + 1.2, dim=1).values
     spec = ops.MLPSpec()
+    eng = _lib.ENGINES[os.environ.get("SPARF_KT_ENGINE", "tc_3x")]
     gs, gc = torch.randn(R, S, device="cuda"), torch.randn(R, S, 3, device="cuda")
 
     def step():
         for p in params:
             p.grad = None
-        s, c = ops.mlp_forward(spec, o, d, t, params, engine=_lib.ENGINE_TC_3X)
+        s, c = ops.mlp_forward(spec, o, d, t, params, engine=eng)
         torch.autograd.backward([s, c], [gs, gc])
 
     def infer():
         with torch.no_grad():
-            ops.mlp_forward(spec, o, d, t, params, engine=_lib.ENGINE_TC_3X)
+            ops.mlp_forward(spec, o, d, t, params, engine=eng)
 
     for name, fn in (("training step (forward with tape + backward)", step), ("inference forward", infer)):
         for _ in range(3):
