@@ -197,7 +197,7 @@ def test_tc_ray_gradients_match_simt(R, S, c2f):
         assert e < 2e-2, (nm, e)   # both sit ~1e-2 from the exact gradient on random nets (2^9 pi amplification)
 
 
-@pytest.mark.parametrize("R,S,c2f", [(1023, 128, None), (300, 96, (0.4, 0.7))])
+@pytest.mark.parametrize("R,S,c2f", [(1023, 128, None), (300, 96, (0.4, 0.7)), (1100, 128, None)])
 def test_tc_3x_w1_reduced_weight_gradient_engine(R, S, c2f):
     """SPARF_ENGINE_TC_3X_W1 (non-default): same forward and same ray gradients as TC_3X, the wide layers' weight / bias
     gradients from ONE bf16 pass over the hi halves of the saved images -- close to TC_3X, but outside the parity bound
