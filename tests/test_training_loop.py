@@ -10,14 +10,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("fine,poses", [(0, 0), (1, 0), (0, 1)])
-def test_training_loop_converges(fine, poses):
+@pytest.mark.parametrize("fine,poses,engine", [(0, 0, "auto"), (1, 0, "auto"), (0, 1, "auto"), (0, 0, "tc_3x_w1"), (0, 1, "tc_3x_w1")])
+def test_training_loop_converges(fine, poses, engine):
     """coarse only / hierarchical / joint pose-NeRF (BARF mask advancing on the device, second fused-Adam group for the
-    9-D pose embeddings)"""
+    9-D pose embeddings); also with the non-default reduced-precision weight-gradient engine (same loss curve to ~1 %)"""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sparf_b200
     import train_synthetic
-    res = train_synthetic.main(["--steps", "300", "--quiet", "--fine", str(fine), "--poses", str(poses), "--rays", "768"])
+    try:
+        res = train_synthetic.main(["--steps", "300", "--quiet", "--fine", str(fine), "--poses", str(poses), "--rays", "768",
+                                    "--engine", engine])
+    finally:
+        sparf_b200.set_engine("auto")
     first, last = res[0], res[1]
-    print("fine=%d poses=%d: loss %.5f -> %.5f" % (fine, poses, first, last))
+    print("fine=%d poses=%d engine=%s: loss %.5f -> %.5f" % (fine, poses, engine, first, last))
     assert last == last and first == first            # finite
     assert last < (0.85 if poses else 0.6) * first, (first, last)

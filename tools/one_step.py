@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""A few taped MLP training steps at the bench shape (1023 rays x 128 samples): the target of the ncu captures."""
+"""A few taped MLP training steps at the bench shape (1023 rays x 128 samples): the target of the ncu captures.
+[SPARF_OS_ENGINE=tc_3x|tc_3x_w1] python tools/one_step.py [steps]"""
 import os
 import sys
 
@@ -28,7 +29,7 @@ def main():
     for _ in range(n):
         for p in params:
             p.grad = None
-        s, c = ops.mlp_forward(spec, o, d, t, params, engine=_lib.ENGINE_TC_3X)
+        s, c = ops.mlp_forward(spec, o, d, t, params, engine=_lib.ENGINES[os.environ.get("SPARF_OS_ENGINE", "tc_3x")])
         torch.autograd.backward([s, c], [gs, gc])
     torch.cuda.synchronize()
 

@@ -33,15 +33,18 @@ def main(argv=None):
     ap.add_argument("--poses", type=int, default=0, help="1: joint pose-NeRF training from perturbed poses (BARF c2f mask)")
     ap.add_argument("--pose-noise", type=float, default=0.03)
     ap.add_argument("--lr-pose", type=float, default=2e-3)
+    ap.add_argument("--engine", default="auto", help="MLP engine (auto | tc_3x | tc_3x_w1 | simt_fp32)")
     ap.add_argument("--quiet", action="store_true")
     args = ap.parse_args(argv)
 
+    import sparf_b200
     from sparf_b200.graphs import GraphedStep
     from sparf_b200.losses import define_loss
     from sparf_b200.optim import FlatParameters, FusedAdam
     from sparf_b200.renderer import Graph
     from sparf_b200.sampling_strategies import RaySamplingStrategy
 
+    sparf_b200.set_engine(args.engine)
     dev = torch.device("cuda")
     B, (H, W) = args.views, args.size
     opt = common.make_opt(S=args.samples, S_fine=args.samples, fine=bool(args.fine), rand_rays=args.rays, stratified=True,
