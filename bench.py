@@ -416,8 +416,8 @@ def run_ours(args):
                     flop_per_launch_group=flop_step_gpu, ms_per_launch_group=group_ms,
                     ms_per_launch_group_eager_events=mlp_ms_per_step,
                     mlp_sample_evals_per_step=evals_per_step,
-                    traffic=TRAFFIC.get(args.config) if args.engine in ("auto", "tc_3x") else None,
-                    traffic_source=TRAFFIC_SOURCE, engine=args.engine)
+                    traffic=TRAFFIC.get((args.engine if args.engine != "auto" else "tc_3x", args.config)),
+                    traffic_source=TRAFFIC_SOURCE.get(args.engine if args.engine != "auto" else "tc_3x"), engine=args.engine)
     cpu = tgb = None
     if world == 1 and not args.no_baselines:   # reported on rank 0 at N = 1 only
         graphed = None
@@ -468,8 +468,9 @@ def shutdown_distributed(dist, grace_s=15.0):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel group of one step, from `ncu --set full` captures
 # (taped forward 1.228 GB, dgrad 1.138 GB, wgrad 2.391 GB at the c2 shape)
-TRAFFIC = {"c2": 4.757e9}
-TRAFFIC_SOURCE = "profiles/r02_ncu_chain.md (ncu --set full of tc_mlp_fwd / dgrad / wgrad, per step)"
+TRAFFIC = {("tc_3x", "c2"): 4.757e9, ("tc_3x_w1", "c2"): 2.582e9}
+TRAFFIC_SOURCE = {"tc_3x": "profiles/r02_ncu_chain.md (ncu --set full of tc_mlp_fwd / dgrad / wgrad, per step)",
+                  "tc_3x_w1": "profiles/r02_ncu_chain_w1.md (ncu --set full of tc_mlp_fwd / dgrad / wgrad, per step)"}
 
 
 # ------------------------------------------------------------------------------------------------ reference arms
