@@ -58,12 +58,8 @@ def load(stack: str = "renderer", shadow_renderer: bool = False) -> SimpleNamesp
             if m not in sys.modules or not isinstance(sys.modules[m], MagicMock):
                 sys.modules[m] = MagicMock()
     if shadow_renderer:
-        import sparf_b200.frequency_nerf as our_nerf
-        import sparf_b200.renderer as our_renderer
-        pkg = importlib.import_module("source.models")
-        sys.modules["source.models.renderer"] = our_renderer
-        sys.modules["source.models.frequency_nerf"] = our_nerf
-        pkg.renderer, pkg.frequency_nerf = our_renderer, our_nerf
+        import sparf_b200
+        sparf_b200.install_as_reference_renderer()     # the product's own one-call swap
     out.renderer = importlib.import_module("source.models.renderer")
     out.frequency_nerf = importlib.import_module("source.models.frequency_nerf")
     out.camera = importlib.import_module("source.utils.camera")
