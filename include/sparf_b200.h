@@ -19,7 +19,7 @@
  *     render passes of one step can share one flat gradient buffer (the caller zeroes it once).
  *
  * Process-level state (all of it): the thread-local error string; a launch counter (sparf_launch_count); per device,
- * lazily: the SM count, the kernels' shared-memory attributes, and ONE internal side stream + two events on which
+ * lazily: the SM count, the kernels' shared-memory attributes, and up to three internal side streams + a few events on which
  * sparf_mlp_backward* runs its small CUDA-core reductions beside the weight-gradient kernel (fork after the dgrad
  * chain, join before the call returns control of `stream`: callers see ordinary stream order, and the pattern is
  * capturable into a CUDA graph).  A workspace must not be shared by calls running concurrently on different streams.

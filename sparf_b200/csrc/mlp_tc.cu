@@ -2195,6 +2195,8 @@ int tc_mlp_forward(const SparfMLP* mlp, int engine, int R, int S, const float* o
 // most thread slots of every SM free).  Event record / wait pairs make the pattern capturable into a CUDA graph.
 struct SideStream {
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr, stream3 = nullptr;   // backward leftovers: three independent chains beside the wgrad kernel
+  cudaEvent_t join2 = nullptr, join3 = nullptr, rayhead = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
   cudaEvent_t raybias = nullptr, packed = nullptr;   // taped forward: raybias ready / backward weight streams packed
   cudaEvent_t sub[8] = {};                           // backward: dgrad of sub-chunk k finished
@@ -2206,6 +2208,11 @@ static SideStream* side_stream() {
   SideStream& s = table[dev & 63];
   if (!s.stream) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s.stream3, cudaStreamNonBlocking) != cudaSuccess) { s.stream = nullptr; return nullptr; }
+    cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join3, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.rayhead, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&s.raybias, cudaEventDisableTiming);
@@ -2446,7 +2453,9 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       return SPARF_OK;
     };
 
-    cudaStream_t sd = st;      // stream of the CUDA-core leftovers (step 4)
+    // streams of the CUDA-core leftovers (steps 4, 5): up to three independent chains, so that together they are shorter
+    // than the weight-gradient kernel they run beside (each is slowed down several-fold while it shares the GPU with it)
+    cudaStream_t sd = st, sd2 = st, sd3 = st;
     if (nsplit <= 1) {
       // A operand in tensor memory (default; SPARF_TC_TMEMA=0 selects the shared-memory-operand kernel): 294 vs 360 us
       if (tmem_a) tc_mlp_dgrad_kernel<true><<<std::min(ntiles, num_sms()), kThreads, kSmemBytes + 1024, st>>>(bp);
@@ -2459,7 +2468,15 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       if (side) {
         SPARF_CHECK_CUDA(cudaEventRecord(side->fork, st));
         SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-        sd = side->stream;
+        sd = sd2 = sd3 = side->stream;
+        // with ray gradients the leftovers (reductions + ray-gradient GEMM + view-direction chain) are longer than the
+        // weight-gradient kernel when serialised: three chains (c3: 4.46 -> 4.39 ms); without them one chain is enough
+        // and measured marginally faster (c2: 1.335 vs 1.345 ms)
+        if (d_origins != nullptr || d_dirs != nullptr) {
+          SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream2, side->fork, 0));
+          SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream3, side->fork, 0));
+          sd2 = side->stream2; sd3 = side->stream3;
+        }
       }
       rc = wgrad_launch(0, ntiles, num_sms() - 1, st);
       if (rc) return rc;
@@ -2504,17 +2521,17 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     image_reduce_kernel<1><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd>>>(one, img, Mc, ntiles, tpb);
     SPARF_CHECK_LAUNCH("image_reduce_kernel<1>");
     one.j[0] = rj[1];
-    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd>>>(one, img, Mc, ntiles, tpb);
+    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd2>>>(one, img, Mc, ntiles, tpb);
     SPARF_CHECK_LAUNCH("image_reduce_kernel<3>");
-    ray_sum_ghid_kernel<<<nr, 128, 0, sd>>>(img, nr, S, c.rayS);
+    ray_sum_ghid_kernel<<<nr, 128, 0, sd2>>>(img, nr, S, c.rayS);
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
-    ray_head_wgrad_kernel<<<ceil_div(nr, 8), 128, 0, sd>>>(nr, 8, c.rayS, c.denc, grad->head_w[0]);
+    ray_head_wgrad_kernel<<<ceil_div(nr, 8), 128, 0, sd2>>>(nr, 8, c.rayS, c.denc, grad->head_w[0]);
     SPARF_CHECK_LAUNCH("ray_head_wgrad_kernel");
 
     // 5. gradients w.r.t. the rays (camera-pose optimisation)
     if (d_origins != nullptr || d_dirs != nullptr) {
       if (!tape) {
-        pack_weights_enc_kernel<<<16, 256, 0, sd>>>(mlp->trunk_w[4], mlp->trunk_w[0], c.packed_e);
+        pack_weights_enc_kernel<<<16, 256, 0, sd3>>>(mlp->trunk_w[4], mlp->trunk_w[0], c.packed_e);
         SPARF_CHECK_LAUNCH("pack_weights_enc_kernel");
       }
       EncGradParams ep;
@@ -2522,12 +2539,16 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       ep.d_origins = d_origins ? d_origins + (size_t)r0 * 3 : nullptr;
       ep.d_dirs = d_dirs ? d_dirs + (size_t)r0 * 3 : nullptr;
       ep.M = Mc; ep.S = S; ep.num_tiles = ntiles;
-      tc_mlp_encgrad_kernel<<<std::min(ntiles, num_sms()), 192, kEgSmem + 1024, sd>>>(ep);
+      tc_mlp_encgrad_kernel<<<std::min(ntiles, num_sms()), 192, kEgSmem + 1024, sd3>>>(ep);
       SPARF_CHECK_LAUNCH("tc_mlp_encgrad_kernel");
       if (d_dirs) {
-        ray_head_dgrad_kernel<<<ceil_div(nr * 32, 256), 256, 0, sd>>>(nr, c.rayS, mlp->head_w[0], c.gdenc);
+        ray_head_dgrad_kernel<<<ceil_div(nr * 32, 256), 256, 0, sd2>>>(nr, c.rayS, mlp->head_w[0], c.gdenc);   // after ray_sum_ghid
         SPARF_CHECK_LAUNCH("ray_head_dgrad_kernel");
-        direnc_bwd_kernel<<<ceil_div(nr, 128), 128, 0, sd>>>(nr, kLv, 32, c.denc, c.gdenc, dirs + (size_t)r0 * 3,
+        if (sd3 != sd2) {   // direnc_bwd adds to d_dirs without atomics: after encgrad (same stream) and after gdenc is ready
+          SPARF_CHECK_CUDA(cudaEventRecord(side->rayhead, sd2));
+          SPARF_CHECK_CUDA(cudaStreamWaitEvent(sd3, side->rayhead, 0));
+        }
+        direnc_bwd_kernel<<<ceil_div(nr, 128), 128, 0, sd3>>>(nr, kLv, 32, c.denc, c.gdenc, dirs + (size_t)r0 * 3,
                                                              d_dirs + (size_t)r0 * 3);
         SPARF_CHECK_LAUNCH("direnc_bwd_kernel");
       }
@@ -2535,6 +2556,12 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     if (side) {   // join: later work on the caller's stream (next chunk, optimiser, ...) sees every gradient
       SPARF_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
       SPARF_CHECK_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+      if (sd2 != sd) {
+        SPARF_CHECK_CUDA(cudaEventRecord(side->join2, sd2));
+        SPARF_CHECK_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
+        SPARF_CHECK_CUDA(cudaEventRecord(side->join3, sd3));
+        SPARF_CHECK_CUDA(cudaStreamWaitEvent(st, side->join3, 0));
+      }
     }
   }
   return SPARF_OK;
