@@ -2558,7 +2558,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     // one launch per job shape (blockIdx.y = job index is passed through the first table entry of each launch)
     ReduceJobs one;
     one.j[0] = rj[0];
-    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd2>>>(one, img, Mc, ntiles, tpb);
+    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd>>>(one, img, Mc, ntiles, tpb);
     SPARF_CHECK_LAUNCH("image_reduce_kernel<3>");
     ray_sum_ghid_kernel<<<nr, 128, 0, sd2>>>(img, nr, S, c.rayS);
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
