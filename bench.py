@@ -17,9 +17,10 @@ One "step" = one pass of the hot path over one synthetic ray batch of a BASELINE
     c5   Replica-shaped 9 views 340x600, 9 x 455 = 4095 rays, hierarchical, pose gradients; STRONG scaling: the batch
          is sharded over the N GPUs, one NCCL all-reduce of [d theta_c | d theta_f | d xi] per step
 
-Timing: W warm-up steps, then K steps, each bracketed by CUDA events on the launching stream with an L2 flush (256 MiB
-memset) between steps; ms_per_step = mean of the K intervals; multi-GPU: barrier + synchronize on both sides and the MAX
-over ranks.  Clocks / throttle reasons are sampled with nvidia-smi during the timed region.  Prints ONE JSON line (rank 0).
+Timing: W warm-up steps, then K steps enqueued back to back between a barrier + synchronize on both sides; every step is
+bracketed by its own CUDA events on the launching stream, with an L2 flush (256 MiB memset) between steps outside the
+event pairs; ms_per_step = mean of the K intervals, MAX over ranks.  (`e2e` additionally waits for each step's loss on the
+host, so there every step starts on an idle device.)  Clocks / throttle reasons are sampled with nvidia-smi during the timed region.  Prints ONE JSON line (rank 0).
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref, made by oracle/build_ref.py) on the host cores
 (`--device cuda`: on the GPU, the torch/cuBLAS path SURVEY 8d calls "the kernel to beat"); without oracle/_ref it
@@ -325,15 +326,20 @@ def run_ours(args):
         return loss
 
     def timed(n_warm, n_steps, e2e, use_graph=False):
-        times = []
+        # device-timed arm: the steps are enqueued BACK TO BACK between two synchronisations (+ barriers), each bracketed
+        # by its own pair of CUDA events on the launching stream with the L2 flush outside the pair; the host runs ahead
+        # of the device like a training loop does, so an idle-GPU launch latency is not part of a step.  End-to-end arm:
+        # the host additionally waits for every step's loss (a caller that reads its result), so each step starts on an
+        # idle device and pays the full launch path.
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        events = []
         for i in range(n_warm + n_steps):
             src = idx_host[(n_total if e2e else 0) + i]
             if not e2e:
                 ray_idx_dev = src.to(dev, non_blocking=True)
             flush.zero_()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if e2e:  # host buffers in, host scalar out, inside the timed region
@@ -342,9 +348,13 @@ def run_ours(args):
             if e2e:
                 loss_host.copy_(loss.detach(), non_blocking=True)
             e1.record()
-            torch.cuda.synchronize()
-            if i >= n_warm:
-                times.append(e0.elapsed_time(e1))
+            if e2e:
+                torch.cuda.synchronize()
+            events.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        times = [a.elapsed_time(b) for a, b in events[n_warm:]]
         t = torch.tensor([sum(times)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -435,7 +445,8 @@ def run_ours(args):
                             l2_flush_between_steps=True,
                             launch="one CUDA-graph replay per step" if launched_as_graph else "eager",
                             eager_ms_per_step=eager_ms_per_step,
-                            timing="mean of per-step CUDA-event intervals, max over ranks",
+                            timing="K steps enqueued back to back between two synchronisations (+ barriers); per-step CUDA-event intervals "
+                                   "on the launching stream, L2 flush between steps outside the intervals; sum, max over ranks",
                             parallelism="dp%d (ray sharding, one NCCL all-reduce of [MLP | pose] grads per step%s)"
                                         % (world, ", captured in the step's CUDA graph" if ar_in_graph else ""),
                             allreduce_us=ar_us, allreduce_bytes=int(flat.numel() * 4)),

@@ -2447,7 +2447,8 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
     bp.w7 = mlp->trunk_w[7]; bp.w9 = mlp->head_w[1];
     bp.M = Mc; bp.num_tiles = ntiles; bp.img = img;
     static const bool tmem_a = !(getenv("SPARF_TC_TMEMA") && getenv("SPARF_TC_TMEMA")[0] == '0');
-    SideStream* side = overlap_small_kernels() ? side_stream() : nullptr;
+    static const bool overlap_bwd = !(getenv("SPARF_TC_OVERLAP_BWD") && getenv("SPARF_TC_OVERLAP_BWD")[0] == '0');
+    SideStream* side = (overlap_small_kernels() && overlap_bwd) ? side_stream() : nullptr;
     // sub-chunk pipeline only with the TMEM-operand chain kernel and when every sub-chunk still fills the GPU
     int nsplit = (side && tmem_a) ? std::min(8, std::max(1, bwd_split_env("SPARF_TC_BWD_SPLIT", kBwdSplitDefault))) : 1;
     while (nsplit > 1 && ntiles / nsplit < num_sms()) --nsplit;
