@@ -348,7 +348,7 @@ def run_ours(args):
             if e2e:
                 loss_host.copy_(loss.detach(), non_blocking=True)
             e1.record()
-            if e2e:
+            if e2e or args.sync_each_step:
                 torch.cuda.synchronize()
             events.append((e0, e1))
         torch.cuda.synchronize()
@@ -657,6 +657,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=list(CONFIGS))
     ap.add_argument("--engine", default="auto")
+    ap.add_argument("--sync-each-step", type=int, default=0,
+                    help="1: synchronise after every timed step (each step then starts on an idle device)")
     ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="reference arm only")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager")
     ap.add_argument("--allreduce-in-graph", type=int, default=1)
