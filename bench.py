@@ -17,10 +17,10 @@ One "step" = one pass of the hot path over one synthetic ray batch of a BASELINE
     c5   Replica-shaped 9 views 340x600, 9 x 455 = 4095 rays, hierarchical, pose gradients; STRONG scaling: the batch
          is sharded over the N GPUs, one NCCL all-reduce of [d theta_c | d theta_f | d xi] per step
 
-Timing: W warm-up steps, then K steps enqueued back to back between a barrier + synchronize on both sides; every step is
-bracketed by its own CUDA events on the launching stream, with an L2 flush (256 MiB memset) between steps outside the
-event pairs; ms_per_step = mean of the K intervals, MAX over ranks.  (`e2e` additionally waits for each step's loss on the
-host, so there every step starts on an idle device.)  Clocks / throttle reasons are sampled with nvidia-smi during the timed region.  Prints ONE JSON line (rank 0).
+Timing: W warm-up steps, then K steps between a barrier + synchronize on both sides; every step is bracketed by its own
+CUDA events on the launching stream, with an L2 flush (256 MiB memset) between steps outside the event pairs and (default)
+a synchronize after each step; ms_per_step = mean of the K intervals, MAX over ranks.  `--sync-each-step 0` enqueues the K
+steps back to back instead.  Clocks / throttle reasons are sampled with nvidia-smi during the timed region.  Prints ONE JSON line (rank 0).
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref, made by oracle/build_ref.py) on the host cores
 (`--device cuda`: on the GPU, the torch/cuBLAS path SURVEY 8d calls "the kernel to beat"); without oracle/_ref it
@@ -326,11 +326,11 @@ def run_ours(args):
         return loss
 
     def timed(n_warm, n_steps, e2e, use_graph=False):
-        # device-timed arm: the steps are enqueued BACK TO BACK between two synchronisations (+ barriers), each bracketed
-        # by its own pair of CUDA events on the launching stream with the L2 flush outside the pair; the host runs ahead
-        # of the device like a training loop does, so an idle-GPU launch latency is not part of a step.  End-to-end arm:
-        # the host additionally waits for every step's loss (a caller that reads its result), so each step starts on an
-        # idle device and pays the full launch path.
+        # every step is bracketed by its own pair of CUDA events on the launching stream with the L2 flush outside the
+        # pair; barrier + synchronize on both sides of the whole loop.  By default the host also synchronises after each
+        # step (--sync-each-step 0: the steps are enqueued back to back; measured 1.364 vs 1.350 ms on the same
+        # power-capped box, the launch latency of a graph replay on an idle device is below the noise).  The
+        # end-to-end arm always waits for every step's loss on the host (a caller that reads its result).
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -445,8 +445,9 @@ def run_ours(args):
                             l2_flush_between_steps=True,
                             launch="one CUDA-graph replay per step" if launched_as_graph else "eager",
                             eager_ms_per_step=eager_ms_per_step,
-                            timing="K steps enqueued back to back between two synchronisations (+ barriers); per-step CUDA-event intervals "
-                                   "on the launching stream, L2 flush between steps outside the intervals; sum, max over ranks",
+                            timing="per-step CUDA-event intervals on the launching stream (L2 flush between steps outside the "
+                                   "intervals, %s), barrier + synchronize on both sides; sum, max over ranks"
+                                   % ("synchronize after every step" if args.sync_each_step else "steps enqueued back to back"),
                             parallelism="dp%d (ray sharding, one NCCL all-reduce of [MLP | pose] grads per step%s)"
                                         % (world, ", captured in the step's CUDA graph" if ar_in_graph else ""),
                             allreduce_us=ar_us, allreduce_bytes=int(flat.numel() * 4)),
@@ -657,8 +658,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=list(CONFIGS))
     ap.add_argument("--engine", default="auto")
-    ap.add_argument("--sync-each-step", type=int, default=0,
-                    help="1: synchronise after every timed step (each step then starts on an idle device)")
+    ap.add_argument("--sync-each-step", type=int, default=1,
+                    help="1 (default): synchronise after every timed step, each step starts on an idle device; 0: the K "
+                         "steps are enqueued back to back (measured ~1 %% slower on a power-capped B200: lower clocks)")
     ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="reference arm only")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager")
     ap.add_argument("--allreduce-in-graph", type=int, default=1)
