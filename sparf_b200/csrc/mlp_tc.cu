@@ -1561,16 +1561,33 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
       float cs[8], xs[8], gsum = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) cs[k] = xs[k] = 0.f;
+      // the row weights of the NEXT stage are fetched before waiting for the current one: a global-load latency inside
+      // the wait -> reduce -> arrive path would delay the recycling of the stage (the ring is only 3 deep)
+      float gq[8], gn[8];
+      auto load_g = [&](int qi, float (&g)[8]) {
+        const long long m0 = (long long)(job.tile_begin + (qi >> 2)) * kTileM + (qi & 3) * 32 + rg * 8;
+        if (m0 + 8 <= job.xrows) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(job.xg + m0));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(job.xg + m0) + 1);
+          g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = (m0 + i < job.xrows) ? __ldg(job.xg + m0 + i) : 0.f;
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gq[i] = gn[i] = 0.f;
+      if (hasx && nq > 0) load_g(0, gq);
       uint32_t stage = 0, phase = 0;
       for (int qi = 0; qi < nq; ++qi) {
+        if (hasx && qi + 1 < nq) load_g(qi + 1, gn);
         mbar_wait(&full[stage], phase);
         if (hasx) {
           const uint8_t* xh = smem + stage * stage_bytes + (x_blk0 + blk) * 4096;
           const uint8_t* xl = xh + 4 * 4096;
-          const long long m0 = (long long)(job.tile_begin + (qi >> 2)) * kTileM + (qi & 3) * 32 + rg * 8;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float g = (m0 + i < job.xrows) ? __ldg(job.xg + m0 + i) : 0.f;
+            const float g = gq[i];
             const uint32_t off = (uint32_t)(rg * 8 + i) * 128u + (uint32_t)((c ^ i) << 4);
             float x[8];
             unpack8(*reinterpret_cast<const uint4*>(xh + off),
@@ -1579,6 +1596,8 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
             for (int k = 0; k < 8; ++k) xs[k] = fmaf(g, x[k], xs[k]);
             if (blk == 0 && c == 0) gsum += g;
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gq[i] = gn[i];
         }
         if (has) {
           const uint8_t* bh = smem + stage * stage_bytes + blk * 4096;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel device time of one MLP training step / inference forward (torch.profiler = CUPTI activity records, no
-replay, warm caches).  Usage: [SPARF_KT_ENGINE=tc_3x|tc_3x_w1] python tools/kernel_times.py [R S]"""
+replay, warm caches).  Usage: [SPARF_KT_ENGINE=tc_3x|tc_3x_w1] [SPARF_KT_NOPOSE=1] python tools/kernel_times.py [R S]"""
 import os
 import sys
 from collections import defaultdict
@@ -22,8 +22,9 @@ def main():
     keys = sum([["mlp_feat.%d.weight" % i, "mlp_feat.%d.bias" % i] for i in range(8)], []) + \
         ["mlp_rgb.0.weight", "mlp_rgb.0.bias", "mlp_rgb.1.weight", "mlp_rgb.1.bias"]
     params = [sd[k].cuda().requires_grad_(True) for k in keys]
-    o = (torch.randn(R, 3, device="cuda") * 0.3).requires_grad_(True)
-    d = torch.nn.functional.normalize(torch.randn(R, 3, device="cuda"), dim=-1).requires_grad_(True)
+    pose = os.environ.get("SPARF_KT_NOPOSE", "0") != "1"      # ray gradients (camera-pose optimisation) on / off
+    o = (torch.randn(R, 3, device="cuda") * 0.3).requires_grad_(pose)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, device="cuda"), dim=-1).requires_grad_(pose)
     t = torch.sort(torch.rand(R, S, device="cuda") * 4 + 1.2, dim=1).values
     spec = ops.MLPSpec()
     eng = _lib.ENGINES[os.environ.get("SPARF_KT_ENGINE", "tc_3x")]
