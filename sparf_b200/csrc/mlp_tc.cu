@@ -1441,12 +1441,6 @@ struct WgradJob {
   float* colsum;         // optional: colsum[f] += sum_rows G[row][f]  (the layer's bias gradient), else NULL
   int passes;            // 3: G_hi X_hi + G_lo X_hi + G_hi X_lo;  1 (SPARF_ENGINE_TC_3X_W1): G_hi X_hi, the lo halves are
                          // not read at all (the bias gradients become column sums of G_hi)
-  // optional narrow output riding on the activation stream (the density row of trunk layer 7, a 256 -> 1 product that is
-  // not worth an MMA): xsum[f] += sum_rows xg[row] * X[row][f], xsum_bias[0] += sum_rows xg[row], rows < xrows
-  float* xsum;
-  float* xsum_bias;
-  const float* xg;
-  long long xrows;
 };
 constexpr int kMaxWgradJobs = 160;
 constexpr int kBwdSplitDefault = 1;     // sub-chunks of the backward pipeline (dgrad(k + 1) beside wgrad(k)); 1 = off
@@ -1557,48 +1551,12 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
       // per thread and stage with conflict-free 16-byte loads (8 consecutive lanes read one swizzled 128-byte row)
       const int blk = warp - 2, c = lane & 7, rg = lane >> 3;
       const bool has = job.colsum && blk < job.mblk;
-      const bool hasx = job.xsum != nullptr && blk < job.nblk;      // reducer warp w also owns activation block w
-      float cs[8], xs[8], gsum = 0.f;
+      float cs[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) cs[k] = xs[k] = 0.f;
-      // the row weights of the NEXT stage are fetched before waiting for the current one: a global-load latency inside
-      // the wait -> reduce -> arrive path would delay the recycling of the stage (the ring is only 3 deep)
-      float gq[8], gn[8];
-      auto load_g = [&](int qi, float (&g)[8]) {
-        const long long m0 = (long long)(job.tile_begin + (qi >> 2)) * kTileM + (qi & 3) * 32 + rg * 8;
-        if (m0 + 8 <= job.xrows) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(job.xg + m0));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(job.xg + m0) + 1);
-          g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = (m0 + i < job.xrows) ? __ldg(job.xg + m0 + i) : 0.f;
-        }
-      };
-#pragma unroll
-      for (int i = 0; i < 8; ++i) gq[i] = gn[i] = 0.f;
-      if (hasx && nq > 0) load_g(0, gq);
+      for (int k = 0; k < 8; ++k) cs[k] = 0.f;
       uint32_t stage = 0, phase = 0;
       for (int qi = 0; qi < nq; ++qi) {
-        if (hasx && qi + 1 < nq) load_g(qi + 1, gn);
         mbar_wait(&full[stage], phase);
-        if (hasx) {
-          const uint8_t* xh = smem + stage * stage_bytes + (x_blk0 + blk) * 4096;
-          const uint8_t* xl = xh + 4 * 4096;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float g = gq[i];
-            const uint32_t off = (uint32_t)(rg * 8 + i) * 128u + (uint32_t)((c ^ i) << 4);
-            float x[8];
-            unpack8(*reinterpret_cast<const uint4*>(xh + off),
-                    one_pass ? make_uint4(0u, 0u, 0u, 0u) : *reinterpret_cast<const uint4*>(xl + off), x);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) xs[k] = fmaf(g, x[k], xs[k]);
-            if (blk == 0 && c == 0) gsum += g;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) gq[i] = gn[i];
-        }
         if (has) {
           const uint8_t* bh = smem + stage * stage_bytes + blk * 4096;
           const uint8_t* bl = bh + 4 * 4096;
@@ -1624,18 +1582,6 @@ __global__ void __launch_bounds__(192, 1) tc_mlp_wgrad_kernel(const __grid_const
           v += __shfl_xor_sync(0xffffffffu, v, 16);
           if (rg == 0) atomicAdd(job.colsum + blk * 64 + c * 8 + k, v);
         }
-      }
-      if (hasx) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float v = xs[k];
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (rg == 0) atomicAdd(job.xsum + blk * 64 + c * 8 + k, v);
-        }
-        gsum += __shfl_xor_sync(0xffffffffu, gsum, 8);
-        gsum += __shfl_xor_sync(0xffffffffu, gsum, 16);
-        if (blk == 0 && lane == 0 && job.xsum_bias) atomicAdd(job.xsum_bias, gsum);
       }
     }
     mbar_wait(done, 0);
@@ -2334,7 +2280,7 @@ int tc_mlp_forward_tape(const SparfMLP* mlp, int engine, int R, int S, const flo
   fill_pack_params(mlp, pp, packed);
   pp.order = fwd_variant(true, 3, true, ntiles) == FWD_TMEM ? 1 : 0;
   pack_weights_kernel<true><<<kChunksPerTile, 1024, 0, st>>>(pp);   // on the forward's critical path: one element group
-                                                                      // per thread (13 -> ~5 us)
+                                                                      // per thread (13 -> ~6 us)
   SPARF_CHECK_LAUNCH("pack_weights_kernel");
   PackParams pb;
   fill_pack_params(mlp, pb, tp + tape_off_packed_b(R, S));
@@ -2489,7 +2435,6 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
           j.tile_end = t_lo + (int)((long long)nt * (sl + 1) / slabs);
           j.dW = dW; j.ldw = ldw; j.col0 = col0; j.enc_cols = enc; j.colsum = colsum;
           j.passes = wg_passes;
-          j.xsum = nullptr; j.xsum_bias = nullptr; j.xg = nullptr; j.xrows = 0;
           jobs[nj++] = j;
         }
       };
@@ -2500,11 +2445,7 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       const int s_lo = std::max(1, ctas / 10), extra = std::max(0, std::min(8, ctas - 10 * s_lo));
       for (int i = 0; i < 10; ++i) slabs[i] = s_lo + (i < extra ? 1 : 0);
       add_jobs(T_GHID, T_FEAT, 2, 4, grad->head_w[0], kW + kEv, 0, 0, slabs[7], grad->head_b[0]);     // head 0, feature part
-      const int nj7 = nj;
       add_jobs(T_G7F, T_H0 + 6, 4, 4, grad->trunk_w[7] + kW, kW, 0, 0, slabs[0], grad->trunk_b[7] + 1);  // trunk 7 rows 1..256
-      for (int i = nj7; i < nj; ++i) {     // ... and row 0 (density) + its bias on the same activation stream (CUDA cores)
-        jobs[i].xsum = grad->trunk_w[7]; jobs[i].xsum_bias = grad->trunk_b[7]; jobs[i].xg = c.g_raw; jobs[i].xrows = Mc;
-      }
       for (int l = 6; l >= 1; --l)
         add_jobs(t_g(l), T_H0 + (l - 1), 4, 4, grad->trunk_w[l], l == 4 ? kW + 63 : kW, 0, 0, slabs[7 - l], grad->trunk_b[l]);
       add_jobs(t_g(4), T_ENC, 4, 1, grad->trunk_w[4], kW + 63, kW, 1, slabs[8], nullptr);             // skip part of layer 4
@@ -2573,13 +2514,16 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
       rj[nrj++] = j;
     };
     // (bias gradients = column sums of the gradient images are produced inside the weight-gradient kernel)
-    // (the density row of trunk 7 rides on the weight-gradient kernel's activation stream as well: WgradJob::xsum)
+    add_red(T_H0 + 6, 4, 1, c.g_raw, 1, grad->trunk_w[7], kW, grad->trunk_b[7]);        // density row of trunk 7
     add_red(T_HID, 2, 3, c.g_pre, 4, grad->head_w[1], kHW, grad->head_b[1]);             // 128 -> 3 colour layer
     const int tpb = 4;
     // one launch per job shape (blockIdx.y = job index is passed through the first table entry of each launch)
     ReduceJobs one;
     one.j[0] = rj[0];
-    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd>>>(one, img, Mc, ntiles, tpb);
+    image_reduce_kernel<1><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd>>>(one, img, Mc, ntiles, tpb);
+    SPARF_CHECK_LAUNCH("image_reduce_kernel<1>");
+    one.j[0] = rj[1];
+    image_reduce_kernel<3><<<dim3(ceil_div(ntiles, tpb), 1), 256, 0, sd2>>>(one, img, Mc, ntiles, tpb);
     SPARF_CHECK_LAUNCH("image_reduce_kernel<3>");
     ray_sum_ghid_kernel<<<nr, 128, 0, sd2>>>(img, nr, S, c.rayS);
     SPARF_CHECK_LAUNCH("ray_sum_ghid_kernel");
