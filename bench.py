@@ -480,7 +480,7 @@ def shutdown_distributed(dist, grace_s=15.0):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the MLP kernel group of one step, from `ncu --set full` captures
 # (taped forward 1.228 GB, dgrad 1.138 GB, wgrad 2.391 GB at the c2 shape)
-TRAFFIC = {("tc_3x", "c2"): 4.757e9, ("tc_3x_w1", "c2"): 2.582e9}
+TRAFFIC = {("tc_3x", "c2"): 4.770e9, ("tc_3x_w1", "c2"): 2.582e9}
 TRAFFIC_SOURCE = {"tc_3x": "profiles/r02_ncu_chain.md (ncu --set full of tc_mlp_fwd / dgrad / wgrad, per step)",
                   "tc_3x_w1": "profiles/r02_ncu_chain_w1.md (ncu --set full of tc_mlp_fwd / dgrad / wgrad, per step)"}
 
