@@ -25,6 +25,7 @@
  * capturable into a CUDA graph).  A workspace must not be shared by calls running concurrently on different streams.
  * Environment knobs, read once, for A/B timing only (defaults are the measured-fastest settings):
  *   SPARF_TC_OVERLAP=0   no side stream (everything on `stream`)
+ *   SPARF_TC_OVERLAP_BWD=0   only the backward's leftovers back on `stream` (the forward's packing stays on the side stream)
  *   SPARF_TC_TMEMA=0     chain kernels with shared-memory A operands (round-1 generation; also serves the single-pass
  *                        engine and the recompute backward)
  *   SPARF_TC_BWD_SPLIT=n, SPARF_TC_BWD_ND=k   backward pipelined in n sub-chunks, dgrad on k SMs beside wgrad (off)
