@@ -236,7 +236,15 @@ def rays_per_view(cfg, rank=0, world=1):
     return n
 
 
+def quiet_nccl_banner():
+    """NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print "NCCL version ..." on STDOUT, in front of the one JSON line
+    this script owes its caller; keep stdout clean (an explicit INFO / TRACE request is left alone)."""
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def run_ours(args):
+    quiet_nccl_banner()
     import sparf_b200
     from sparf_b200 import _lib, ops
     from sparf_b200.distributed import FlatGradients, shard_range
