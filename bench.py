@@ -240,7 +240,7 @@ def quiet_nccl_banner():
     """NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print "NCCL version ..." on STDOUT, in front of the one JSON line
     this script owes its caller; keep stdout clean (an explicit INFO / TRACE request is left alone)."""
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+        del os.environ["NCCL_DEBUG"]       # (WARN would still print the banner: every level >= VERSION does)
 
 
 def run_ours(args):
