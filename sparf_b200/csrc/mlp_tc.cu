@@ -2474,7 +2474,8 @@ static int tc_mlp_backward_impl(const SparfMLP* mlp, int engine, int R, int S, c
         // with ray gradients the leftovers (reductions + ray-gradient GEMM + view-direction chain) are longer than the
         // weight-gradient kernel when serialised: three chains (c3: 4.46 -> 4.39 ms); without them one chain is enough
         // and measured marginally faster (c2: 1.335 vs 1.345 ms)
-        if (d_origins != nullptr || d_dirs != nullptr) {
+        // (the single-pass weight-gradient kernel is short enough that the serial chain outlasts it even without them)
+        if (d_origins != nullptr || d_dirs != nullptr || wg_passes == 1) {
           SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream2, side->fork, 0));
           SPARF_CHECK_CUDA(cudaStreamWaitEvent(side->stream3, side->fork, 0));
           sd2 = side->stream2; sd3 = side->stream3;
